@@ -1,0 +1,202 @@
+/* vmgb.h -- C ABI of libvmgb.so, the sm_100a kernel library under the VMG model-forward hot path.
+ *
+ * The reference (EasyVision-Ton/VMG) is pure Python/PyTorch: it has NO FFI for this path; its seam is
+ * the nn.Module contract of models/vmg.py:176-210,585-637 (kept by vmg_b200/model.py).  This header
+ * is the boundary BELOW that module: one entry point per fused kernel family.  Each prototype
+ * cites the reference call site(s) it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative VMGB_E* code; nothing throws, nothing
+ *     allocates, nothing synchronises; `stream` is a cudaStream_t passed as void*.
+ *   - all data pointers are caller-owned DEVICE pointers; activations are channels-last
+ *     ("NHWC": [images, H, W, C], C contiguous).  `*_dt` arguments are VMGB_F32 / VMGB_BF16.
+ *   - `pitch` arguments are the distance in ELEMENTS between consecutive pixels of a tensor
+ *     (>= its channel count), so kernels can read/write channel slices of wider buffers.
+ *   - arithmetic is fp32 (CUDA-core kernels) or bf16 x bf16 -> fp32 (tcgen05 kernels); statistics,
+ *     softmaxes and coordinate math are always fp32.
+ *
+ * Prototype grammar is deliberately trivial (one line per argument type: const void*, void*, int,
+ * long long, float): vmg_b200/ops.py parses THIS FILE to build its ctypes signatures, and
+ * tests/test_abi.py checks that every symbol declared here is exported.
+ */
+#ifndef VMGB_H_
+#define VMGB_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMGB_OK            0
+#define VMGB_EINVAL       -1   /* bad shape / unsupported argument combination */
+#define VMGB_EUNSUPPORTED -2   /* valid request that this build has no kernel for */
+#define VMGB_ECUDA        -3   /* CUDA runtime error; see vmgb_last_cuda_error() */
+#define VMGB_EARCH        -4   /* device is not sm_100 */
+
+#define VMGB_F32  0
+#define VMGB_BF16 1
+
+/* activation codes for the conv / GEMM epilogue */
+#define VMGB_ACT_NONE    0
+#define VMGB_ACT_RELU    1
+#define VMGB_ACT_LRELU   2   /* slope = act_alpha */
+#define VMGB_ACT_GELU    3   /* exact erf form (torch.nn.GELU default) */
+#define VMGB_ACT_SIGMOID 4
+
+/* epilogue modes:  v = act(acc + bias) * out_scale
+ *   STORE : out = v
+ *   RESADD: out = res + res_scale * v
+ *   GATE  : out = res + res_scale * ((aux + v) * tanh(v))       (function.py:796-802 + :1215) */
+#define VMGB_EPI_STORE  0
+#define VMGB_EPI_RESADD 1
+#define VMGB_EPI_GATE   2
+
+int         vmgb_version(void);
+const char* vmgb_arch(void);                 /* "sm_100a" */
+int         vmgb_last_cuda_error(void);      /* last cudaError_t seen by this library */
+const char* vmgb_last_cuda_error_string(void);
+int         vmgb_device_check(void);         /* VMGB_OK iff current device is compute capability 10.x */
+long long   vmgb_launch_count(void);         /* kernels launched by this library since load */
+
+/* ---- conv2d / linear, CUDA-core fp32 path -------------------------------------------------
+ * Replaces every nn.Conv2d / nn.Linear call on the path: F.conv2d stride 1,
+ * "same" zero padding, kernel R x S in {1,3,7}, `groups`; a Linear is R=S=1 over H=1,W=rows.
+ * x [n_img,H,W,(x_pitch)] ; w fp32 packed [groups][R*S][Cin/groups][Cout/groups] ; bias fp32[Cout] or NULL.
+ * pixel_shuffle=2 stores as nn.PixelShuffle(2) would (vmg.py:629-630): out is [n_img,2H,2W,Cout/4].
+ * res / aux (may be NULL) are addressed like `out`.
+ * "virtual concat": n_src in {1,2,3} equally wide sources x, x1, x2 (same dtype and pitch) are read as
+ * torch.cat([x, x1, x2], channel) would be, without materialising it (trajectory.py:372,457,476);
+ * Cin is the TOTAL; requires groups == 1 and (Cin/n_src) % 16 == 0 when n_src > 1. */
+int vmgb_conv2d_nhwc(const void* x, const void* x1, const void* x2, int n_src, int x_dt, int x_pitch,
+                     const void* w, const void* bias,
+                     void* out, int out_dt, int out_pitch,
+                     const void* res, int res_dt, int res_pitch,
+                     const void* aux, int aux_dt, int aux_pitch,
+                     int n_img, int H, int W, int Cin, int Cout, int R, int S, int groups,
+                     int act, float act_alpha, float out_scale, int epi, float res_scale,
+                     int pixel_shuffle, void* stream);
+
+/* ---- conv2d / linear, tcgen05 + TMEM + TMA path (bf16 operands, fp32 accumulate) -----------
+ * Same contract as vmgb_conv2d_nhwc; x must be bf16 with x_pitch % 8 == 0; w is bf16 packed
+ * [groups][R*S][Cout/groups][Kp], Kp = roundup(Cin/groups, 16) zero padded (see vmgb_pack_weight_tc). */
+int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2, int n_src, int x_pitch,
+                        const void* w, int Kp, const void* bias,
+                        void* out, int out_dt, int out_pitch,
+                        const void* res, int res_dt, int res_pitch,
+                        const void* aux, int aux_dt, int aux_pitch,
+                        int n_img, int H, int W, int Cin, int Cout, int R, int S, int groups,
+                        int act, float act_alpha, float out_scale, int epi, float res_scale,
+                        int pixel_shuffle, int variant, void* stream);
+
+/* OIHW fp32 conv weight [Cout][Cin/groups][R][S] (or Linear [Cout][Cin], R=S=1) -> packed layouts. */
+int vmgb_pack_weight(const void* w_oihw, void* w_packed, int Cout, int Cin_g, int R, int S, int groups, void* stream);
+int vmgb_pack_weight_tc(const void* w_oihw, void* w_packed_bf16, int Cout, int Cin_g, int Kp, int R, int S, int groups, void* stream);
+
+/* ---- LayerNorm over C (eps 1e-5, biased variance): function.py:1164,1195 ; layers.py:768-775 */
+int vmgb_layernorm(const void* x, int x_dt, void* out, int out_dt, const void* gamma, const void* beta,
+                   long long rows, int C, float eps, void* stream);
+
+/* ---- Morph-FC chunk permutation (function.py:763-785, closed form SURVEY.md A.2) -------------
+ * axis 0 = H branch, 1 = W branch.  inverse=0: x[BT,H,W,C] -> A[rows, Cp] (zero padded rows/channels);
+ * inverse=1: Y[rows, Cp] -> y[BT,H,W,C] (cropped).  Cp = ceil(C/chunk)*chunk,
+ * rows = BT * ceil(L/chunk)*chunk * other, L = H (axis 0) or W (axis 1). */
+int vmgb_morph_permute(const void* src, int src_dt, void* dst, int dst_dt,
+                       int BT, int H, int W, int C, int chunk, int axis, int inverse, void* stream);
+
+/* ---- grouped channel sums (fp32 out, must be zeroed by the caller).  function.py:791 (TAB global
+ * mean over T,H,W per sample), :546-558 (CALayer per-frame pool).  Rows are laid out as
+ * [n_seg][groups][seg_rows]: out[g][c] = scale * sum_{s,r} (a+b+c)[(s*groups + g)*seg_rows + r][c].
+ * (frames are stored time-major [T,B,...]: per-sample sums use n_seg=T, groups=B, seg_rows=H*W.) */
+int vmgb_channel_sum(const void* a, const void* b, const void* c, int dt, float* out,
+                     int n_seg, int groups, long long seg_rows, int C, float scale, void* stream);
+
+/* softmax over the 3 branch weights: logits fp32 [B][3C] with feature index 3*c+j (function.py:792)
+ * -> a fp32 [B][3][C] */
+int vmgb_softmax3(const float* logits, float* a, int B, int C, void* stream);
+
+/* mix = h*a0 + w*a1 + c*a2 (function.py:793); a fp32 [B][3][C]; rows [n_seg][B][seg_rows] as above. */
+int vmgb_mix3(const void* h, const void* w, const void* c, int dt, const float* a, void* out, int out_dt,
+              int n_seg, int B, long long seg_rows, int C, void* stream);
+
+/* RCAB tail (function.py:556-558,578-581 and scale_c): out = (u * y[frame][c] + x) * scale */
+int vmgb_ca_apply(const void* u, const void* x, int dt, const float* y, void* out, int out_dt,
+                  int frames, long long rows_per_frame, int C, float scale, void* stream);
+
+/* elementwise out = a + b */
+int vmgb_add(const void* a, const void* b, int dt, void* out, int out_dt, long long n, void* stream);
+
+/* W *= gamma in place, fp32 (function.py:765-768,778-781) */
+int vmgb_decay_weights(float* w, const float* gamma, long long n, void* stream);
+
+/* ---- flow warps (trajectory.py:71-116 + ATen grid_sampler_2d, align_corners=True, border) ----
+ * feature warp: bilinear; x,out [n,h,w,C]; flow fp32 [n,h,w,2] (dx,dy).
+ * location warp: nearest; loc fp32 [n,h,w,2*K] in, [n,h,w,(out_pitch)] out, `K2` = 2*K channels moved. */
+int vmgb_flow_warp_bilinear(const void* x, int x_dt, int x_pitch, const float* flow, void* out, int out_dt, int out_pitch,
+                            int n, int h, int w, int C, void* stream);
+int vmgb_flow_warp_nearest(const float* loc, int in_pitch, const float* flow, float* out, int out_pitch,
+                           int n, int h, int w, int K2, void* stream);
+/* writes the identity grid (x, y) into channels [c0, c0+2) of loc [n,h,w,pitch] (trajectory.py:316-317,365) */
+int vmgb_loc_identity(float* loc, int pitch, int c0, int n, int h, int w, void* stream);
+
+/* flow smoothing (function.py:1466-1478): reflect-pad to a multiple of r, r x r mean, nearest x r, crop.
+ * in / out: fp32 channels-last [n,h,w,2] (out must not alias in). */
+int vmgb_flow_smooth(const float* flow_in, float* out_nhwc, int n, int h, int w, int r, void* stream);
+
+/* L2-normalise each pixel over C (F.normalize eps 1e-12): trajectory.py:744-749 */
+int vmgb_l2norm(const void* x, int x_dt, int x_pitch, void* out, int out_dt, long long rows, int C, void* stream);
+
+/* ---- LTAM 'wins' attention (trajectory.py:672-795,534-547) ---------------------
+ * q      [n,h,w,C]            L2-normalised current features
+ * keys   [Kcap][n,h,w,C]      L2-normalised key-frame stage inputs   (first K used)
+ * vals   [Kcap][n,h,w,C]      key-frame propagated features
+ * loc    fp32 [n,h,w,loc_pitch] tracked (x,y) per key-frame, channels 2k,2k+1
+ * rel    fp32 [heads][4][4], decay fp32 [heads]
+ * out    [n,h,w,C]  attention output BEFORE the proj Linear (proj + anchor add = conv2d RESADD) */
+int vmgb_ltam_wins(const void* q, const void* keys, const void* vals, int dt, long long kv_stride,
+                   const float* loc, int loc_pitch, const float* rel, const float* decay,
+                   void* out, int out_dt, int n, int h, int w, int C, int heads, int K, void* stream);
+
+/* ---- resampling (layers.py:777-798): pixel-(un)shuffle gather + LayerNorm fused; Linear follows.
+ * down: x[BT,H,W,C] -> out[BT,H/2,W/2,4C] feature (neiw,neih,c);  up: x[BT,H,W,C] -> out[BT,2H,2W,C/4].
+ * `add` (may be NULL) is summed to x first (skip adds of vmg.py:530-543). */
+int vmgb_resample_ln(const void* x, const void* add, int dt, void* out, int out_dt, const void* gamma, const void* beta,
+                     int BT, int H, int W, int C, int up, float eps, void* stream);
+
+/* ---- mdsc shortcut pieces (vmg.py:389-400,519,525) */
+int vmgb_maxpool4(const void* x, int dt, void* out, int out_dt, int BT, int H, int W, int C, void* stream);
+/* per-frame GroupNorm(1,C)+ReLU given per-frame sums: stats fp32 [frames][2] = (sum, sum of squares) */
+int vmgb_frame_stats(const void* x, int dt, float* stats, int frames, long long elems_per_frame, void* stream);
+int vmgb_groupnorm1_relu(const void* x, int dt, const float* stats, const void* gamma, const void* beta, void* out, int out_dt,
+                         int frames, long long rows_per_frame, int C, float eps, void* stream);
+
+/* ---- SPyNet helpers (vmg.py:39-123) : all fp32 channels-last ----------------------------------
+ * prep: padded frames NHWC [n,H,W,3] -> bilinear resize (align_corners=False) to [n,h_up,w_up,3], then
+ *       (v - mean)/std  (vmg.py:104-110 then :43-44); every frame is prepared once and shared by all pairs */
+int vmgb_spynet_prep(const float* frames, float* out, float m0, float m1, float m2, float s0, float s1, float s2,
+                     int n, int H, int W, int h_up, int w_up, void* stream);
+/* avg_pool2d(2,2) pyramid step (vmg.py:47-59) */
+int vmgb_avgpool2(const float* x, float* out, int n, int H, int W, int C, void* stream);
+/* one pyramid level (vmg.py:65-83): pyr [T*B,h,w,3] time-major; pair p = t*B+b: dir 0 -> ref = frame p+B,
+ * supp = frame p (forward flow, vmg.py:458), dir 1 -> ref = p, supp = p+B (backward flow, :460).
+ * flow_up = 2*bilinear_x2(flow_coarse [pairs,h/2,w/2,2], align_corners=True) (zeros when NULL);
+ * out8 [pairs,h,w,8] = cat[ref, warp_border(supp, flow_up), flow_up]; flow_up [pairs,h,w,2] also stored. */
+int vmgb_spynet_level_input(const float* pyr, const float* flow_coarse, float* out8, float* flow_up,
+                            int n_pairs, int B, int dir, int h, int w, void* stream);
+/* final: bilinear resize (align_corners=False) of flow [n,h_up,w_up,2] to [n,h,w,2] and rescale (vmg.py:113-121) */
+int vmgb_flow_resize(const float* flow, float* out, int n, int h_up, int w_up, int h, int w, void* stream);
+
+/* ---- input / output layout kernels (vmg.py:590-599,635-636) ------------------------------------
+ * Inside the library frames are stored TIME-MAJOR [T,B,...] so that one recurrent step of the
+ * trajectory sweep (all clips of the batch at frame t) is one contiguous image batch.
+ * pad_input   : x NCHW fp32 [B,T,3,H,W] -> NHWC fp32 [T,B,Hp,Wp,3], replicate padded (vmg.py:596-599)
+ * mirror_check: *sumsq += sum |x[:, :T/2] - flip(x[:, T/2:])|^2   (vmg.py:426-432; mirror iff == 0)
+ * final_output: out NCHW fp32 [B, t0..t0+Tc, 3,4H,4W] = y NHWC [Tc,B,4H,4W,3 (pitch)] + bilinear_x4(x)
+ *               (trilinear with unit depth scale == per-frame bilinear, align_corners=False; vmg.py:593,636) */
+int vmgb_pad_input(const float* x, float* out, int B, int T, int H, int W, int Hp, int Wp, void* stream);
+int vmgb_mirror_check(const float* x, float* sumsq, int B, int T, long long frame_elems, void* stream);
+int vmgb_final_output(const void* y, int y_dt, int y_pitch, const float* x, float* out, int B, int T, int t0, int Tc,
+                      int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMGB_H_ */

@@ -1,0 +1,241 @@
+// conv_generic.cu -- CUDA-core (fp32 FFMA) implicit-GEMM convolution / linear with the fused epilogue
+// menu.  This is the strict-fp32 path (parity gate 1e-4) and the fallback for shapes the tcgen05
+// kernel does not take (Cin=3, SPyNet 7x7 in fp32).  Replaces F.conv2d / F.linear call sites listed in
+// SURVEY.md section 2.3 (trajectory.py:26-52, function.py:50-79, vmg.py:126-173,378-385 ...).
+//
+// Tiling: CTA = 128 pixels x 64 output channels, K step 16 input channels of one tap, 256 threads,
+// each thread owns an 8 (pixels) x 4 (channels) register tile.
+#include "common.cuh"
+
+namespace vmgb {
+
+struct ConvP {
+  const void* x; const void* x1; const void* x2; int n_src; int Csrc; const float* w; const float* bias; void* out; const void* res; const void* aux;
+  int x_pitch, out_dt, out_pitch, res_dt, res_pitch, aux_dt, aux_pitch;
+  int n_img, H, W, Cin_g, Cout_g, R, S, groups;
+  int act; float alpha, out_scale; int epi; float res_scale; int ps;
+  long long M;
+};
+
+constexpr int BM = 128, BN = 64, BK = 16;
+
+template <typename TIN>
+__device__ __forceinline__ void load8(const TIN* p, int valid, float* v) {
+  // loads up to 8 consecutive input channels (zero beyond `valid`)
+  if (valid >= 8) {
+    if (sizeof(TIN) == 4) {
+      if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        return;
+      }
+    } else {
+      if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        uint4 r = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+        return;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < valid) {
+      if (sizeof(TIN) == 4) v[j] = reinterpret_cast<const float*>(p)[j];
+      else v[j] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[j]);
+    } else v[j] = 0.f;
+  }
+}
+
+template <typename TIN>
+__global__ void __launch_bounds__(256) conv_generic_kernel(ConvP p) {
+  __shared__ __align__(16) float As[BK][BM];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int t = threadIdx.x;
+  const int g = blockIdx.z;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  // A-load role: pixel lp, channels [lk, lk+8) of the K step
+  const int lp = t & 127, lk = (t >> 7) * 8;
+  const long long lm = m0 + lp;
+  const bool lvalid = lm < p.M;
+  int li = 0, lh = 0, lw = 0;
+  if (lvalid) { li = (int)(lm / ((long long)p.H * p.W)); int rem = (int)(lm - (long long)li * p.H * p.W); lh = rem / p.W; lw = rem - lh * p.W; }
+  // B-load role
+  const int bk = t >> 4, bn4 = (t & 15) * 4;
+  const bool bvec = (p.Cout_g & 3) == 0;
+  // compute role
+  const int tx = t & 15, ty = t >> 4;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const TIN* xsrc[3] = {reinterpret_cast<const TIN*>(p.x), reinterpret_cast<const TIN*>(p.x1), reinterpret_cast<const TIN*>(p.x2)};
+  const int padr = p.R / 2, pads = p.S / 2;
+  const int taps = p.R * p.S;
+  for (int tap = 0; tap < taps; ++tap) {
+    const int dr = tap / p.S - padr, ds = tap % p.S - pads;
+    const int hh = lh + dr, ww = lw + ds;
+    const bool pv = lvalid && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;
+    const long long xoff = (((long long)li * p.H + hh) * p.W + ww) * p.x_pitch + (long long)g * p.Cin_g;
+    const float* wp = p.w + ((long long)(g * taps + tap) * p.Cin_g) * p.Cout_g;
+    for (int c0 = 0; c0 < p.Cin_g; c0 += BK) {
+      float av[8];
+      int valid = pv ? min(8, p.Cin_g - (c0 + lk)) : 0;
+      // virtual concat: the K step [c0, c0+16) lies inside one source (Csrc % 16 == 0)
+      const int si = p.n_src > 1 ? c0 / p.Csrc : 0;
+      const TIN* xp = xsrc[si] + xoff - (long long)si * p.Csrc;
+      if (valid > 0) load8<TIN>(xp + c0 + lk, valid, av);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) av[j] = 0.f;
+      }
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      {
+        const int kk = c0 + bk, nn = n0 + bn4;
+        if (kk < p.Cin_g) {
+          const float* q = wp + (long long)kk * p.Cout_g + nn;
+          if (bvec && nn + 3 < p.Cout_g) bv = *reinterpret_cast<const float4*>(q);
+          else {
+            if (nn < p.Cout_g) bv.x = q[0];
+            if (nn + 1 < p.Cout_g) bv.y = q[1];
+            if (nn + 2 < p.Cout_g) bv.z = q[2];
+            if (nn + 3 < p.Cout_g) bv.w = q[3];
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) As[lk + j][lp] = av[j];
+      *reinterpret_cast<float4*>(&Bs[bk][bn4]) = bv;
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+        float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+      }
+    }
+  }
+
+  // ---- epilogue -------------------------------------------------------------------------------
+  const int Cout = p.Cout_g * p.groups;
+  const int ncol0 = n0 + tx * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long m = m0 + ty * 8 + i;
+    if (m >= p.M) continue;
+    long long opix = m;       // output pixel index (row of the output tensor)
+    int oi = 0, oh = 0, ow = 0;
+    if (p.ps == 2) { oi = (int)(m / ((long long)p.H * p.W)); int rem = (int)(m - (long long)oi * p.H * p.W); oh = rem / p.W; ow = rem - oh * p.W; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ng = ncol0 + j;
+      if (ng >= p.Cout_g) continue;
+      const int co = g * p.Cout_g + ng;
+      float v = acc[i][j] + (p.bias ? p.bias[co] : 0.f);
+      v = apply_act(v, p.act, p.alpha) * p.out_scale;
+      int oc = co;
+      if (p.ps == 2) {
+        oc = co >> 2;
+        const int dy = (co >> 1) & 1, dx = co & 1;
+        opix = ((long long)oi * (2 * p.H) + (2 * oh + dy)) * (2 * p.W) + (2 * ow + dx);
+      }
+      if (p.epi == VMGB_EPI_RESADD) {
+        v = ldf(p.res, p.res_dt, opix * p.res_pitch + oc) + p.res_scale * v;
+      } else if (p.epi == VMGB_EPI_GATE) {
+        const float a = ldf(p.aux, p.aux_dt, opix * p.aux_pitch + oc);
+        v = ldf(p.res, p.res_dt, opix * p.res_pitch + oc) + p.res_scale * ((a + v) * tanhf(v));
+      }
+      stf(p.out, p.out_dt, opix * p.out_pitch + oc, v);
+    }
+  }
+  (void)Cout;
+}
+
+// OIHW fp32 -> [G][R*S][Cin_g][Cout_g] fp32
+__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ o, int Cout, int Cin_g, int taps, int groups) {
+  const int Cout_g = Cout / groups;
+  const long long total = (long long)Cout * Cin_g * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int n = (int)(i % Cout_g); long long r = i / Cout_g;
+    int ci = (int)(r % Cin_g); r /= Cin_g;
+    int tap = (int)(r % taps); int g = (int)(r / taps);
+    o[i] = w[((long long)(g * Cout_g + n) * Cin_g + ci) * taps + tap];
+  }
+}
+
+// OIHW fp32 -> [G][R*S][Cout_g][Kp] bf16 (zero padded K)
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout, int Cin_g, int Kp, int taps, int groups) {
+  const int Cout_g = Cout / groups;
+  const long long total = (long long)groups * taps * Cout_g * Kp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i % Kp); long long r = i / Kp;
+    int n = (int)(r % Cout_g); r /= Cout_g;
+    int tap = (int)(r % taps); int g = (int)(r / taps);
+    float v = k < Cin_g ? w[((long long)(g * Cout_g + n) * Cin_g + k) * taps + tap] : 0.f;
+    o[i] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace vmgb
+
+using namespace vmgb;
+
+extern "C" int vmgb_conv2d_nhwc(const void* x, const void* x1, const void* x2, int n_src, int x_dt, int x_pitch, const void* w, const void* bias,
+                                void* out, int out_dt, int out_pitch,
+                                const void* res, int res_dt, int res_pitch,
+                                const void* aux, int aux_dt, int aux_pitch,
+                                int n_img, int H, int W, int Cin, int Cout, int R, int S, int groups,
+                                int act, float act_alpha, float out_scale, int epi, float res_scale,
+                                int pixel_shuffle, void* stream) {
+  if (!x || !w || !out || !dt_ok(x_dt) || !dt_ok(out_dt)) return VMGB_EINVAL;
+  if (n_img <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || groups <= 0) return VMGB_EINVAL;
+  if (Cin % groups || Cout % groups || !(R & 1) || !(S & 1)) return VMGB_EINVAL;
+  if (epi != VMGB_EPI_STORE && (!res || !dt_ok(res_dt))) return VMGB_EINVAL;
+  if (epi == VMGB_EPI_GATE && (!aux || !dt_ok(aux_dt))) return VMGB_EINVAL;
+  if (pixel_shuffle != 0 && (pixel_shuffle != 2 || (Cout & 3))) return VMGB_EINVAL;
+  if (n_src < 1 || n_src > 3 || (n_src > 1 && (!x1 || groups != 1 || Cin % n_src || (Cin / n_src) % BK))) return VMGB_EINVAL;
+  if (n_src > 2 && !x2) return VMGB_EINVAL;
+  ConvP p;
+  p.x1 = x1; p.x2 = x2; p.n_src = n_src; p.Csrc = Cin / n_src;
+  p.x = x; p.w = (const float*)w; p.bias = (const float*)bias; p.out = out; p.res = res; p.aux = aux;
+  p.x_pitch = x_pitch; p.out_dt = out_dt; p.out_pitch = out_pitch; p.res_dt = res_dt; p.res_pitch = res_pitch;
+  p.aux_dt = aux_dt; p.aux_pitch = aux_pitch;
+  p.n_img = n_img; p.H = H; p.W = W; p.Cin_g = Cin / groups; p.Cout_g = Cout / groups; p.R = R; p.S = S; p.groups = groups;
+  p.act = act; p.alpha = act_alpha; p.out_scale = out_scale; p.epi = epi; p.res_scale = res_scale; p.ps = pixel_shuffle;
+  p.M = (long long)n_img * H * W;
+  long long mt = (p.M + BM - 1) / BM;
+  if (mt > 2147483647LL) return VMGB_EINVAL;
+  dim3 grid((unsigned)mt, (p.Cout_g + BN - 1) / BN, groups);
+  if (x_dt == VMGB_F32) conv_generic_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(p);
+  else conv_generic_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(p);
+  return check_launch();
+}
+
+extern "C" int vmgb_pack_weight(const void* w_oihw, void* w_packed, int Cout, int Cin_g, int R, int S, int groups, void* stream) {
+  if (!w_oihw || !w_packed || Cout % groups) return VMGB_EINVAL;
+  long long total = (long long)Cout * Cin_g * R * S;
+  int blocks = (int)((total + 255) / 256); if (blocks > 4096) blocks = 4096;
+  pack_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>((const float*)w_oihw, (float*)w_packed, Cout, Cin_g, R * S, groups);
+  return check_launch();
+}
+
+extern "C" int vmgb_pack_weight_tc(const void* w_oihw, void* w_packed_bf16, int Cout, int Cin_g, int Kp, int R, int S, int groups, void* stream) {
+  if (!w_oihw || !w_packed_bf16 || Cout % groups || Kp < Cin_g || (Kp & 7)) return VMGB_EINVAL;
+  long long total = (long long)Cout * Kp * R * S;
+  int blocks = (int)((total + 255) / 256); if (blocks > 4096) blocks = 4096;
+  pack_weight_tc_kernel<<<blocks, 256, 0, as_stream(stream)>>>((const float*)w_oihw, (__nv_bfloat16*)w_packed_bf16, Cout, Cin_g, Kp, R * S, groups);
+  return check_launch();
+}

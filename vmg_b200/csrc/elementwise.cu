@@ -1,0 +1,371 @@
+// elementwise.cu -- the HBM-bound row kernels of the TAB / resampling / shortcut path.
+// All kernels: channels-last rows, fp32 math, f32 or bf16 storage.  References per entry point are in
+// include/vmgb.h.
+#include "common.cuh"
+
+namespace vmgb {
+
+constexpr int MAXV = 32;  // per-lane register tile: rows up to 32*32 = 1024 channels
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* x, int x_dt, void* out, int out_dt,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[MAXV];
+  const long long base = row * C;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) { const int c = lane + 32 * i; v[i] = c < C ? ldf(x, x_dt, base + c) : 0.f; s += v[i]; }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) { const int c = lane + 32 * i; const float d = c < C ? v[i] - mean : 0.f; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) { const int c = lane + 32 * i; if (c < C) stf(out, out_dt, base + c, (v[i] - mean) * rstd * gamma[c] + beta[c]); }
+}
+
+// L2 normalise (F.normalize, eps 1e-12)
+__global__ void __launch_bounds__(256) l2norm_kernel(const void* x, int x_dt, int x_pitch, void* out, int out_dt,
+                                                     long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) { const int c = lane + 32 * i; v[i] = c < C ? ldf(x, x_dt, row * x_pitch + c) : 0.f; s += v[i] * v[i]; }
+  const float inv = 1.f / fmaxf(sqrtf(warp_sum(s)), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) { const int c = lane + 32 * i; if (c < C) stf(out, out_dt, row * C + c, v[i] * inv); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Morph-FC chunk permutation.  Token/feature maps (function.py:763-785):
+//   axis 0: row = ((bt*W + w)*(Hp/ch) + hg)*ch + g ; f = r*S + s ; src x[bt, hg*ch + r, w, g*S + s]
+//   axis 1: row = ((bt*H + h)*(Wp/ch) + wg)*ch + g ; f = r*S + s ; src x[bt, h, wg*ch + r, g*S + s]
+// ---------------------------------------------------------------------------------------------
+__global__ void morph_gather_kernel(const void* x, int x_dt, void* A, int a_dt, int BT, int H, int W, int C,
+                                    int ch, int axis, long long total) {
+  const int Cp = (C + ch - 1) / ch * ch, S = Cp / ch;
+  const int L = axis == 0 ? H : W, Lg = (L + ch - 1) / ch, O = axis == 0 ? W : H;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % Cp); long long row = i / Cp;
+    const int g = (int)(row % ch); row /= ch;
+    const int lg = (int)(row % Lg); row /= Lg;
+    const int o = (int)(row % O); const int bt = (int)(row / O);
+    const int r = f / S, s = f - r * S;
+    const int l = lg * ch + r, c = g * S + s;
+    float v = 0.f;
+    if (l < L && c < C) {
+      const int h = axis == 0 ? l : o, w = axis == 0 ? o : l;
+      v = ldf(x, x_dt, (((long long)bt * H + h) * W + w) * C + c);
+    }
+    stf(A, a_dt, i, v);
+  }
+}
+
+__global__ void morph_scatter_kernel(const void* Y, int y_dt, void* out, int out_dt, int BT, int H, int W, int C,
+                                     int ch, int axis, long long total) {
+  const int Cp = (C + ch - 1) / ch * ch, S = Cp / ch;
+  const int L = axis == 0 ? H : W, Lg = (L + ch - 1) / ch, O = axis == 0 ? W : H;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C); long long pix = i / C;
+    const int w = (int)(pix % W); pix /= W;
+    const int h = (int)(pix % H); const int bt = (int)(pix / H);
+    const int l = axis == 0 ? h : w, o = axis == 0 ? w : h;
+    const int lg = l / ch, r = l - lg * ch, g = c / S, s = c - g * S;
+    const long long row = (((long long)bt * O + o) * Lg + lg) * ch + g;
+    stf(out, out_dt, i, ldf(Y, y_dt, row * Cp + r * S + s));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// grouped channel sums (atomic accumulation of per-block partials into a zeroed fp32 buffer)
+// grid = (row chunks, groups); block = 256 threads = 8 row lanes x 32 channel lanes
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) channel_sum_kernel(const void* a, const void* b, const void* c, int dt, float* out,
+                                                          int n_groups, long long rows_per_group, int C, float scale, int rows_per_block) {
+  __shared__ float part[8][33];
+  // blockIdx.y = segment*n_groups + group ; rows_per_group here = rows of ONE segment
+  const int g = blockIdx.y % n_groups;
+  const long long seg_base = (long long)blockIdx.y * rows_per_group;
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows_per_group, r0 + rows_per_block);
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int ch = c0 + cl;
+    float s = 0.f;
+    if (ch < C) {
+      for (long long r = r0 + rl; r < r1; r += 8) {
+        const long long idx = (seg_base + r) * C + ch;
+        float v = ldf(a, dt, idx);
+        if (b) v += ldf(b, dt, idx);
+        if (c) v += ldf(c, dt, idx);
+        s += v;
+      }
+    }
+    part[rl][cl] = s;
+    __syncthreads();
+    if (rl == 0 && ch < C) {
+      float tot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot += part[k][cl];
+      atomicAdd(out + (long long)g * C + ch, tot * scale);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void softmax3_kernel(const float* __restrict__ logits, float* __restrict__ a, int B, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  const float* l = logits + (long long)b * 3 * C + 3 * c;
+  const float m = fmaxf(l[0], fmaxf(l[1], l[2]));
+  const float e0 = expf(l[0] - m), e1 = expf(l[1] - m), e2 = expf(l[2] - m);
+  const float inv = 1.f / (e0 + e1 + e2);
+  float* o = a + (long long)b * 3 * C + c;
+  o[0] = e0 * inv; o[C] = e1 * inv; o[2 * C] = e2 * inv;
+}
+
+__global__ void mix3_kernel(const void* h, const void* w, const void* c, int dt, const float* __restrict__ a, void* out, int out_dt,
+                            int B, long long rows_per_b, int C, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % C);
+    const long long row = i / C;
+    const int b = (int)((row / rows_per_b) % B);
+    const float* ab = a + (long long)b * 3 * C + ch;
+    stf(out, out_dt, i, ldf(h, dt, i) * ab[0] + ldf(w, dt, i) * ab[C] + ldf(c, dt, i) * ab[2 * C]);
+  }
+}
+
+__global__ void ca_apply_kernel(const void* u, const void* x, int dt, const float* __restrict__ y, void* out, int out_dt,
+                                long long rows_per_frame, int C, float scale, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % C);
+    const long long fr = (i / C) / rows_per_frame;
+    stf(out, out_dt, i, (ldf(u, dt, i) * y[fr * C + ch] + ldf(x, dt, i)) * scale);
+  }
+}
+
+__global__ void add_kernel(const void* a, const void* b, int dt, void* out, int out_dt, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    stf(out, out_dt, i, ldf(a, dt, i) + ldf(b, dt, i));
+}
+
+__global__ void decay_kernel(float* __restrict__ w, const float* __restrict__ g, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    w[i] = w[i] * g[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// resampling gather + LayerNorm (layers.py:777-798): one warp per OUTPUT row
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resample_ln_kernel(const void* x, const void* add, int dt, void* out, int out_dt,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          int BT, int H, int W, int C, int up, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int Ho = up ? 2 * H : H / 2, Wo = up ? 2 * W : W / 2, F = up ? C / 4 : 4 * C;
+  if (row >= (long long)BT * Ho * Wo) return;
+  const int wo = (int)(row % Wo); const long long t = row / Wo; const int ho = (int)(t % Ho); const int bt = (int)(t / Ho);
+  float v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int f = lane + 32 * i;
+    v[i] = 0.f;
+    if (f >= F) continue;
+    long long idx;
+    if (!up) {   // f = (neiw*2 + neih)*C + c
+      const int q = f / C, c = f - q * C, neiw = q >> 1, neih = q & 1;
+      idx = (((long long)bt * H + (2 * ho + neih)) * W + (2 * wo + neiw)) * C + c;
+    } else {     // source channel (neiw*2 + neih)*(C/4) + f
+      const int neih = ho & 1, neiw = wo & 1;
+      idx = (((long long)bt * H + (ho >> 1)) * W + (wo >> 1)) * C + (neiw * 2 + neih) * F + f;
+    }
+    float val = ldf(x, dt, idx);
+    if (add) val += ldf(add, dt, idx);
+    v[i] = val; s += val;
+  }
+  const float mean = warp_sum(s) / (float)F;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) { const int f = lane + 32 * i; const float d = f < F ? v[i] - mean : 0.f; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / (float)F + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) { const int f = lane + 32 * i; if (f < F) stf(out, out_dt, row * F + f, (v[i] - mean) * rstd * gamma[f] + beta[f]); }
+}
+
+__global__ void maxpool4_kernel(const void* x, int dt, void* out, int out_dt, int BT, int H, int W, int C, long long total) {
+  const int Ho = H / 4, Wo = W / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C); long long p = i / C;
+    const int wo = (int)(p % Wo); p /= Wo; const int ho = (int)(p % Ho); const int bt = (int)(p / Ho);
+    float m = -INFINITY;
+    for (int dy = 0; dy < 4; ++dy)
+      for (int dx = 0; dx < 4; ++dx)
+        m = fmaxf(m, ldf(x, dt, (((long long)bt * H + 4 * ho + dy) * W + 4 * wo + dx) * C + c));
+    stf(out, out_dt, i, m);
+  }
+}
+
+// per-frame (sum, sum of squares) -> stats[frame][2]; grid = (chunks, frames)
+__global__ void __launch_bounds__(256) frame_stats_kernel(const void* x, int dt, float* stats, long long elems, int elems_per_block) {
+  __shared__ float sh[2][8];
+  const int fr = blockIdx.y;
+  const long long e0 = (long long)blockIdx.x * elems_per_block, e1 = min(elems, e0 + elems_per_block);
+  float s = 0.f, q = 0.f;
+  for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) { const float v = ldf(x, dt, (long long)fr * elems + e); s += v; q += v * v; }
+  s = warp_sum(s); q = warp_sum(q);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ts = 0.f, tq = 0.f;
+    for (int k = 0; k < 8; ++k) { ts += sh[0][k]; tq += sh[1][k]; }
+    atomicAdd(stats + 2 * fr, ts);
+    atomicAdd(stats + 2 * fr + 1, tq);
+  }
+}
+
+__global__ void groupnorm1_relu_kernel(const void* x, int dt, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, void* out, int out_dt, long long rows_per_frame, int C,
+                                       float eps, long long total) {
+  const float cnt = (float)(rows_per_frame * C);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long fr = (i / C) / rows_per_frame;
+    const float mean = stats[2 * fr] / cnt;
+    const float var = fmaxf(stats[2 * fr + 1] / cnt - mean * mean, 0.f);
+    const float v = (ldf(x, dt, i) - mean) * rsqrtf(var + eps) * gamma[c] + beta[c];
+    stf(out, out_dt, i, fmaxf(v, 0.f));
+  }
+}
+
+inline int grid_for(long long total, int threads = 256, int cap = 148 * 16) {
+  long long b = (total + threads - 1) / threads;
+  if (b < 1) b = 1;
+  return (int)(b > cap ? cap : b);
+}
+
+}  // namespace vmgb
+
+using namespace vmgb;
+
+extern "C" int vmgb_layernorm(const void* x, int x_dt, void* out, int out_dt, const void* gamma, const void* beta,
+                              long long rows, int C, float eps, void* stream) {
+  if (!x || !out || !gamma || !beta || !dt_ok(x_dt) || !dt_ok(out_dt) || C <= 0 || C > 32 * MAXV || rows <= 0) return VMGB_EINVAL;
+  long long blocks = (rows + 7) / 8;
+  layernorm_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, x_dt, out, out_dt, (const float*)gamma, (const float*)beta, rows, C, eps);
+  return check_launch();
+}
+
+extern "C" int vmgb_l2norm(const void* x, int x_dt, int x_pitch, void* out, int out_dt, long long rows, int C, void* stream) {
+  if (!x || !out || !dt_ok(x_dt) || !dt_ok(out_dt) || C <= 0 || C > 32 * MAXV || rows <= 0) return VMGB_EINVAL;
+  long long blocks = (rows + 7) / 8;
+  l2norm_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, x_dt, x_pitch, out, out_dt, rows, C);
+  return check_launch();
+}
+
+extern "C" int vmgb_morph_permute(const void* src, int src_dt, void* dst, int dst_dt, int BT, int H, int W, int C, int chunk,
+                                  int axis, int inverse, void* stream) {
+  if (!src || !dst || !dt_ok(src_dt) || !dt_ok(dst_dt) || chunk <= 0 || (axis != 0 && axis != 1)) return VMGB_EINVAL;
+  const int Cp = (C + chunk - 1) / chunk * chunk;
+  const int L = axis == 0 ? H : W, Lp = (L + chunk - 1) / chunk * chunk, O = axis == 0 ? W : H;
+  if (!inverse) {
+    long long total = (long long)BT * Lp * O * Cp;
+    morph_gather_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(src, src_dt, dst, dst_dt, BT, H, W, C, chunk, axis, total);
+  } else {
+    long long total = (long long)BT * H * W * C;
+    morph_scatter_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(src, src_dt, dst, dst_dt, BT, H, W, C, chunk, axis, total);
+  }
+  return check_launch();
+}
+
+extern "C" int vmgb_channel_sum(const void* a, const void* b, const void* c, int dt, float* out, int n_seg, int groups,
+                                long long seg_rows, int C, float scale, void* stream) {
+  if (!a || !out || !dt_ok(dt) || groups <= 0 || n_seg <= 0 || seg_rows <= 0 || C <= 0) return VMGB_EINVAL;
+  if ((long long)n_seg * groups > 65535) return VMGB_EINVAL;
+  int rpb = 256;
+  long long chunks = (seg_rows + rpb - 1) / rpb;
+  while (chunks * groups * n_seg > 148LL * 32 && rpb < (1 << 20)) { rpb *= 2; chunks = (seg_rows + rpb - 1) / rpb; }
+  dim3 grid((unsigned)chunks, n_seg * groups);
+  channel_sum_kernel<<<grid, 256, 0, as_stream(stream)>>>(a, b, c, dt, out, groups, seg_rows, C, scale, rpb);
+  return check_launch();
+}
+
+extern "C" int vmgb_softmax3(const float* logits, float* a, int B, int C, void* stream) {
+  if (!logits || !a || B <= 0 || C <= 0) return VMGB_EINVAL;
+  softmax3_kernel<<<(B * C + 255) / 256, 256, 0, as_stream(stream)>>>(logits, a, B, C);
+  return check_launch();
+}
+
+extern "C" int vmgb_mix3(const void* h, const void* w, const void* c, int dt, const float* a, void* out, int out_dt, int n_seg,
+                         int B, long long seg_rows, int C, void* stream) {
+  if (!h || !w || !c || !a || !out || !dt_ok(dt) || !dt_ok(out_dt) || n_seg <= 0 || B <= 0) return VMGB_EINVAL;
+  long long total = (long long)n_seg * B * seg_rows * C;
+  mix3_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(h, w, c, dt, a, out, out_dt, B, seg_rows, C, total);
+  return check_launch();
+}
+
+extern "C" int vmgb_ca_apply(const void* u, const void* x, int dt, const float* y, void* out, int out_dt, int frames,
+                             long long rows_per_frame, int C, float scale, void* stream) {
+  if (!u || !x || !y || !out || !dt_ok(dt) || !dt_ok(out_dt)) return VMGB_EINVAL;
+  long long total = (long long)frames * rows_per_frame * C;
+  ca_apply_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(u, x, dt, y, out, out_dt, rows_per_frame, C, scale, total);
+  return check_launch();
+}
+
+extern "C" int vmgb_add(const void* a, const void* b, int dt, void* out, int out_dt, long long n, void* stream) {
+  if (!a || !b || !out || !dt_ok(dt) || !dt_ok(out_dt) || n <= 0) return VMGB_EINVAL;
+  add_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(a, b, dt, out, out_dt, n);
+  return check_launch();
+}
+
+extern "C" int vmgb_decay_weights(float* w, const float* gamma, long long n, void* stream) {
+  if (!w || !gamma || n <= 0) return VMGB_EINVAL;
+  decay_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(w, gamma, n);
+  return check_launch();
+}
+
+extern "C" int vmgb_resample_ln(const void* x, const void* add, int dt, void* out, int out_dt, const void* gamma,
+                                const void* beta, int BT, int H, int W, int C, int up, float eps, void* stream) {
+  if (!x || !out || !gamma || !beta || !dt_ok(dt) || !dt_ok(out_dt)) return VMGB_EINVAL;
+  if (up ? (C & 3) : ((H & 1) || (W & 1))) return VMGB_EINVAL;
+  const int F = up ? C / 4 : 4 * C;
+  if (F > 32 * MAXV) return VMGB_EINVAL;
+  const long long rows = up ? (long long)BT * 4 * H * W : (long long)BT * (H / 2) * (W / 2);
+  resample_ln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(x, add, dt, out, out_dt, (const float*)gamma,
+                                                                               (const float*)beta, BT, H, W, C, up, eps);
+  return check_launch();
+}
+
+extern "C" int vmgb_maxpool4(const void* x, int dt, void* out, int out_dt, int BT, int H, int W, int C, void* stream) {
+  if (!x || !out || !dt_ok(dt) || !dt_ok(out_dt) || (H & 3) || (W & 3)) return VMGB_EINVAL;
+  long long total = (long long)BT * (H / 4) * (W / 4) * C;
+  maxpool4_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, dt, out, out_dt, BT, H, W, C, total);
+  return check_launch();
+}
+
+extern "C" int vmgb_frame_stats(const void* x, int dt, float* stats, int frames, long long elems_per_frame, void* stream) {
+  if (!x || !stats || !dt_ok(dt) || frames <= 0 || elems_per_frame <= 0) return VMGB_EINVAL;
+  int epb = 8192;
+  dim3 grid((unsigned)((elems_per_frame + epb - 1) / epb), frames);
+  frame_stats_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, dt, stats, elems_per_frame, epb);
+  return check_launch();
+}
+
+extern "C" int vmgb_groupnorm1_relu(const void* x, int dt, const float* stats, const void* gamma, const void* beta, void* out,
+                                    int out_dt, int frames, long long rows_per_frame, int C, float eps, void* stream) {
+  if (!x || !stats || !gamma || !beta || !out || !dt_ok(dt) || !dt_ok(out_dt)) return VMGB_EINVAL;
+  long long total = (long long)frames * rows_per_frame * C;
+  groupnorm1_relu_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, dt, stats, (const float*)gamma, (const float*)beta, out,
+                                                                        out_dt, rows_per_frame, C, eps, total);
+  return check_launch();
+}

@@ -1,0 +1,523 @@
+"""VMG -- drop-in for the reference `models/vmg.py:VMG` on its forward hot path, running on libvmgb.
+
+Same constructor (models/vmg.py:177-210), same `state_dict` keys/shapes, same
+`forward(x[B,T,3,H,W]) -> [B,T,3,4H,4W]` including the reference's in-place Morph-FC weight decay
+(models/function.py:765-781).  The nn.Modules below only HOLD parameters under the reference's names;
+all arithmetic is issued from `VMG.forward` as vmgb_* kernels (vmg_b200/ops.py).  Unsupported
+constructor values raise NotImplementedError at construction -- there is no fallback path.
+
+Internal layout: channels-last, frames time-major: activations are [T*B, H, W, C].
+"""
+from fractions import Fraction
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops as _ops
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter holders (names mirror the reference module tree)
+# ---------------------------------------------------------------------------------------------
+class _ConvModule(nn.Module):          # mmcv.cnn.ConvModule as used at vmg.py:131-170 (key `.conv`)
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, 7, 1, 3)
+        nn.init.kaiming_normal_(self.conv.weight, a=0, mode='fan_out', nonlinearity='relu')
+        nn.init.constant_(self.conv.bias, 0)
+
+
+class _SPyNetBasicModule(nn.Module):   # vmg.py:126-173
+    def __init__(self):
+        super().__init__()
+        ch = [8, 32, 64, 32, 16, 2]
+        self.basic_module = nn.Sequential(*[_ConvModule(ch[i], ch[i + 1]) for i in range(5)])
+
+
+class _SPyNet(nn.Module):              # vmg.py:18-37
+    def __init__(self):
+        super().__init__()
+        self.basic_module = nn.ModuleList([_SPyNetBasicModule() for _ in range(6)])
+        self.register_buffer('mean', torch.Tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
+        self.register_buffer('std', torch.Tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
+
+
+class _InputProj(nn.Module):           # layers.py:674-717
+    def __init__(self, cin, dim):
+        super().__init__()
+        self.proj = nn.Sequential(nn.Conv2d(cin, dim, 3, 1, 1), nn.LeakyReLU(inplace=True))
+
+
+class _CALayer(nn.Module):             # function.py:542-558
+    def __init__(self, c, reduction):
+        super().__init__()
+        self.conv_du = nn.Sequential(nn.Conv2d(c, c // reduction, 1), nn.ReLU(inplace=True),
+                                     nn.Conv2d(c // reduction, c, 1), nn.Sigmoid())
+
+
+class _RCAB(nn.Module):                # function.py:561-583
+    def __init__(self, c, reduction=8):
+        super().__init__()
+        self.body = nn.Sequential(nn.Conv2d(c, c, 3, 1, 1), nn.ReLU(True), nn.Conv2d(c, c, 3, 1, 1),
+                                  _CALayer(c, reduction))
+
+
+class _Mlp(nn.Module):                 # function.py:30-47
+    def __init__(self, cin, hidden, cout):
+        super().__init__()
+        self.fc1 = nn.Linear(cin, hidden)
+        self.fc2 = nn.Linear(hidden, cout)
+
+
+def _form_decay(chunk, S):
+    """gamma buffer of Enhanced_MorphFCs_decay (function.py:651-732): entry ((m,s),(i,s')) =
+    mean_k d_k^(|m-i|+1), d_k = 1 - 2^(-5-(chunk-1-k)), powers built by repeated multiplication."""
+    d = torch.log(1 - 2 ** (-5 - torch.arange(chunk - 1, -1, -1, dtype=torch.float))).exp()
+    p = d.unsqueeze(-1).repeat(1, chunk)
+    for i in range(1, chunk):
+        p[:, i] = p[:, i] * p[:, i - 1]
+    idx = (torch.arange(chunk)[:, None] - torch.arange(chunk)[None, :]).abs()
+    G = p[:, idx]                                            # [k, m, i]
+    G = G[:, :, None, :, None].expand(chunk, chunk, S, chunk, S).reshape(chunk, chunk * S, chunk * S)
+    return torch.mean(G, 0)
+
+
+class _MorphFC(nn.Module):             # Enhanced_MorphFCs_decay, function.py:596-741
+    def __init__(self, dim, chunk_h, chunk_w, qkv_bias, channel_mixer):
+        super().__init__()
+        self.chunk_h, self.chunk_w = chunk_h, chunk_w
+        self.Ch = int(math.ceil(dim / chunk_h)) * chunk_h
+        self.Cw = int(math.ceil(dim / chunk_w)) * chunk_w
+        self.mlp_h = nn.Sequential(nn.Linear(self.Ch, self.Ch, bias=qkv_bias), nn.ReLU())
+        self.mlp_w = nn.Sequential(nn.Linear(self.Cw, self.Cw, bias=qkv_bias), nn.ReLU())
+        if channel_mixer == 'vanilla':
+            self.mlp_c = nn.Sequential(nn.Linear(dim, dim, bias=qkv_bias), nn.ReLU())
+        else:
+            self.mlp_c = _RCAB(dim)
+        self.reweight = _Mlp(dim, dim // 4, dim * 3)
+        self.proj = nn.Linear(dim, dim)
+        self.register_buffer('gamma_h', _form_decay(chunk_h, self.Ch // chunk_h))
+        self.register_buffer('gamma_w', _form_decay(chunk_w, self.Cw // chunk_w))
+
+
+class _MlpCnn(nn.Module):              # function.py:50-79
+    def __init__(self, dim, ratio, groups):
+        super().__init__()
+        self.hidden = int(dim * ratio)
+        self.fc1 = nn.Conv2d(dim, self.hidden, 3, 1, 1, groups=groups)
+        self.fc2 = nn.Linear(self.hidden, dim)
+
+
+class _TAB(nn.Module):                 # function.py:1139-1217
+    def __init__(self, dim, chunk_h, chunk_w, ratio, groups, qkv_bias, channel_mixer):
+        super().__init__()
+        self.norm2 = nn.LayerNorm(dim)
+        self.spatial_mixing = _MorphFC(dim, chunk_h, chunk_w, qkv_bias, channel_mixer)
+        self.norm3 = nn.LayerNorm(dim)
+        self.channel_mixing = _MlpCnn(dim, ratio, groups)
+
+
+class _LTAM(nn.Module):                # trajectory.py:493-531
+    def __init__(self, dim, heads, twins):
+        super().__init__()
+        self.proj = nn.Linear(dim, dim)
+        self.relative_pos_encoding = nn.Parameter(torch.zeros(heads, twins[0] * twins[1], twins[0] * twins[1]))
+        nn.init.trunc_normal_(self.relative_pos_encoding, std=.02)
+        self.register_buffer('decay_v', 1 - 2 ** (-5 - torch.arange(heads - 1, -1, -1, dtype=torch.float32)))
+
+
+class _ResBlock(nn.Module):            # trajectory.py:165-221
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = nn.Conv2d(c, c, 3, 1, 1)
+        self.conv2 = nn.Conv2d(c, c, 3, 1, 1)
+
+
+class _ResBlocks(nn.Module):           # trajectory.py:16-52
+    def __init__(self, cin, c, n):
+        super().__init__()
+        self.main = nn.Sequential(nn.Conv2d(cin, c, 3, 1, 1), nn.LeakyReLU(0.1, inplace=True),
+                                  nn.Sequential(*[_ResBlock(c) for _ in range(n)]))
+
+
+class _Trajectory(nn.Module):          # trajectory.py:226-272
+    def __init__(self, dim, n_blocks, heads, twins):
+        super().__init__()
+        self.LTAM = _LTAM(dim, heads, twins)
+        self.resblocks = _ResBlocks(2 * dim, dim, n_blocks)
+        self.fusion = nn.Conv2d(3 * dim, dim, 1, 1, 0)
+
+
+class _Stage(nn.Module):               # Mlp_encoder, function.py:1267-1395
+    def __init__(self, dim, depth, chunk_h, chunk_w, ratio, groups, qkv_bias, channel_mixer, local_fuse,
+                 aligned, res_n, heads, twins, key_stride):
+        super().__init__()
+        self.dim, self.chunk_h, self.chunk_w = dim, chunk_h, chunk_w
+        self.key_stride, self.heads = key_stride, heads
+        if local_fuse:
+            self.local_cnn = nn.Conv2d(dim, dim, 3, 1, 1)
+        self.mlp_blocks = nn.ModuleList([_TAB(dim, chunk_h, chunk_w, ratio, groups, qkv_bias, channel_mixer)
+                                         for _ in range(depth)])
+        self.has_traj = aligned is False
+        self.traj_mixing = _Trajectory(dim, res_n, heads, twins) if self.has_traj else nn.Identity()
+
+
+class _Resample(nn.Module):            # UpdownkeepSampling, layers.py:761-775
+    def __init__(self, cin, cout, mode):
+        super().__init__()
+        self.mode = mode
+        f = cin * 4 if mode == 'down' else cin // 4
+        self.norm = nn.LayerNorm(f)
+        self.linear = nn.Linear(f, cout)
+
+
+# ---------------------------------------------------------------------------------------------
+class VMG(nn.Module):
+    """See module docstring.  Extra keyword (not in the reference): `precision` = 'bf16' (tcgen05 path,
+    bf16 activations, fp32 statistics/flows) or 'fp32' (strict fp32 CUDA-core path)."""
+
+    def __init__(self, in_chans=3, embed_dim=[112, 224, 224, 448, 448, 224, 224, 112],
+                 depths=[8, 8, 8, 8, 8, 8, 8, 8], num_heads=[2, 4, 8, 16, 16, 8, 4, 2], num_frames=7,
+                 window_sizes=[(4, 4)] * 8, mdsc=True, if_concat=False, mlp_ratio=4., n_groups=1,
+                 qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.1,
+                 norm_layer=nn.LayerNorm, patch_norm=True, back_RBs=0, spynet_pretrained=None,
+                 image_size=[64, 112], is_train=True, if_print=False, ltam=True,
+                 traj_win=[16, None, None, None], traj_keyframes_n=[3, None, None, None],
+                 traj_heads=[4, None, None, None], temporal_type=[False, None, None, None],
+                 temporal_empty=True, traj_res_n=[1, 0, 0, 0, 0, 0, 1], deform_groups=[8, 16, 16, 32],
+                 max_residual_scale=[1, 2, 2, 4], spatial_type=[False, False, False, False],
+                 flow_smooth=True, smooth_region_range=4, retention_decay=True, non_linear=True,
+                 gating=True, symm=True, symm_act=nn.Tanh, relu_scale=True, relu_scale_norm=False,
+                 ffn_type='vanilla', mixer_type=['mbconv', 'mbconv', 'mlps', 'mlps'], mixer_n=[2, 3, None, None],
+                 r_scaling=1., chunk_ratios=[1 / 4, 1 / 4, 3 / 16, 1 / 8], traj_mode='wins', twins=[2, 2],
+                 traj_scale=True, traj_refine=None, m_scaling=1., if_local_fuse=False, channel_mixer='vanilla',
+                 precision='bf16'):
+        super().__init__()
+        self.num_layers = len(depths)
+        self.num_enc_layers = self.num_layers // 2 + 1
+        self.num_dec_layers = self.num_layers // 2
+        self.scale = 2 ** (self.num_enc_layers - 1)
+        self.embed_dim = embed_dim
+        self.num_in_frames = num_frames
+        self.num_out_frames = num_frames
+        self.is_train = is_train
+        self.init_H, self.init_W = image_size
+        self.frames_mirror = False
+        self.precision = precision
+        if precision not in ('bf16', 'fp32'):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+
+        # ---- value set of the two shipped model families; anything else is refused ----
+        def refuse(cond, what):
+            if cond:
+                raise NotImplementedError(f'vmg_b200.VMG: {what} is outside the supported hot path')
+        n_e = self.num_enc_layers
+        refuse(self.num_layers % 2 == 0 or self.num_layers < 3, 'an even number of stages')
+        refuse(spynet_pretrained is None, 'spynet=None (the trajectory module indexes the flows unconditionally)')
+        refuse(any(m != 'mlps' for m in mixer_type[:n_e]), "mixer_type != 'mlps'")
+        refuse(any(t for t in temporal_type[:n_e]), 'temporal_type=True (DCN alignment)')
+        refuse(not temporal_empty, 'temporal_empty=False (3D window attention)')
+        refuse(relu_scale_norm or not relu_scale, 'relu_scale_norm=True / relu_scale=False')
+        refuse(ffn_type != 'ffn_cnn', "ffn_type != 'ffn_cnn'")
+        refuse(traj_mode != 'wins' or list(twins) != [2, 2], "traj_mode != 'wins' or twins != [2,2]")
+        refuse(if_concat, 'if_concat=True')
+        refuse(back_RBs > 0, 'back_RBs > 0')
+        refuse(not (retention_decay and non_linear and gating and symm), 'retention_decay/non_linear/gating/symm=False')
+        refuse(symm_act not in ('tanh', nn.Tanh), "symm_act != 'tanh'")
+        refuse(not ltam or not traj_scale or traj_refine is not None, 'ltam=False / traj_scale=False / traj_refine')
+        refuse(channel_mixer not in ('vanilla', 'rcab'), f'channel_mixer={channel_mixer!r}')
+        refuse(temporal_type[0] is not False, 'a first stage without trajectory alignment')
+        self.flow_smooth, self.region = flow_smooth, smooth_region_range
+        self.r_scaling, self.m_scaling = float(r_scaling), float(m_scaling)
+        self.n_groups, self.twins = n_groups, list(twins)
+        self.channel_mixer = channel_mixer
+
+        self.chunk_ratio = [float(Fraction(r)) for r in chunk_ratios]
+        self.chunk_h = [int(self.init_H * r) for r in self.chunk_ratio]
+        self.chunk_w = [int(self.init_W * r) for r in self.chunk_ratio]
+
+        self.spynet = _SPyNet()
+        # `spynet_pretrained` is a URL/path in the reference (mmcv load_checkpoint); there is no network
+        # here -- SPyNet weights arrive through load_state_dict like every other parameter.
+        self.local_fuse = if_local_fuse
+        if if_local_fuse:
+            self.local_cnn = nn.Conv2d(embed_dim[0], embed_dim[0], 3, 1, 1)
+        self.input_proj = _InputProj(in_chans, embed_dim[0])
+
+        def make_stage(li, j):
+            return _Stage(embed_dim[li], depths[li], self.chunk_h[j], self.chunk_w[j], mlp_ratio, n_groups, qkv_bias,
+                          channel_mixer, if_local_fuse, temporal_type[j], traj_res_n[li], traj_heads[j], self.twins,
+                          traj_keyframes_n[j])
+        self.encoder_layers = nn.ModuleList()
+        self.upsample = nn.ModuleList()
+        self.downsample = nn.ModuleList()
+        for i in range(n_e):
+            self.encoder_layers.append(make_stage(i, i))
+            if i != n_e - 1:
+                self.downsample.append(_Resample(embed_dim[i], embed_dim[i + 1], 'down'))
+            else:
+                self.upsample.append(_Resample(embed_dim[i], embed_dim[i + 1], 'up'))
+        self.decoder_layers = nn.ModuleList()
+        for i in range(self.num_dec_layers):
+            self.decoder_layers.append(make_stage(i + n_e, -i - 2))
+            if i != self.num_dec_layers - 1:
+                self.upsample.append(_Resample(embed_dim[i + n_e], embed_dim[i + n_e + 1], 'up'))
+
+        self.upconv1 = nn.Conv2d(embed_dim[-1], embed_dim[-1] * 4, 3, 1, 1)
+        self.upconv2 = nn.Conv2d(embed_dim[-1], 64 * 4, 3, 1, 1)
+        self.HRconv = nn.Conv2d(64, 64, 3, 1, 1)
+        self.conv_last = nn.Conv2d(64, 3, 3, 1, 1)
+        self.mdsc = bool(mdsc) and self.num_layers > 3
+        refuse(bool(mdsc) and self.num_layers == 5, 'mdsc with 5 stages')
+        if self.mdsc:
+            self.sc_64_16 = nn.Sequential(nn.Conv2d(embed_dim[0], embed_dim[2], 1), nn.GroupNorm(1, embed_dim[2]), nn.ReLU())
+            self.sc_32_8 = nn.Sequential(nn.Conv2d(embed_dim[1], embed_dim[3], 1), nn.GroupNorm(1, embed_dim[3]), nn.ReLU())
+
+        self.mlp_wd_param = [p for name, p in self.named_parameters() if '.mlp_blocks.' in name]
+        self.apply(self._init_weights)
+        self._packed = {}
+        self.recon_chunk = 8     # frames per reconstruction-head chunk (bounds the 4x-resolution temporaries)
+
+    @staticmethod
+    def _init_weights(m):               # vmg.py:415-424
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    # -------------------------------------------------------------------------------------------
+    # weights
+    # -------------------------------------------------------------------------------------------
+    @property
+    def _adt(self):
+        return torch.bfloat16 if self.precision == 'bf16' else torch.float32
+
+    def _pc(self, mod, groups=1, tc=None, force=False):
+        """Packed kernel-side weights of a Conv2d/Linear holder, re-packed when the parameter changed."""
+        w = mod.weight
+        tc = (self.precision == 'bf16') if tc is None else tc
+        key = id(mod)
+        ver = (w._version, w.data_ptr(), mod.bias._version if mod.bias is not None else -1, tc)
+        ent = self._packed.get(key)
+        if force or ent is None or ent[0] != ver:
+            ent = (ver, _ops.pack_conv(w, mod.bias, groups, tc=tc))
+            self._packed[key] = ent
+        return ent[1]
+
+    # -------------------------------------------------------------------------------------------
+    # SPyNet (vmg.py:39-123, 435-464) -- fp32 end to end; only the level-0 flows are consumed
+    # -------------------------------------------------------------------------------------------
+    def _compute_flow(self, xp, B, T, mirror):
+        o = _ops
+        N, Hp, Wp, _ = xp.shape
+        hu = Hp if Hp % 32 == 0 else 32 * (Hp // 32 + 1)
+        wu = Wp if Wp % 32 == 0 else 32 * (Wp // 32 + 1)
+        if not hasattr(self, '_meanstd') or self._meanstd[0] != (self.spynet.mean._version, self.spynet.std._version):
+            self._meanstd = ((self.spynet.mean._version, self.spynet.std._version),
+                             self.spynet.mean.flatten().tolist(), self.spynet.std.flatten().tolist())
+        pyr = [o.spynet_prep(xp, self._meanstd[1], self._meanstd[2], hu, wu)]
+        for _ in range(5):
+            pyr.append(o.avgpool2(pyr[-1]))
+        pyr = pyr[::-1]
+        n_pairs = (T - 1) * B
+        flows = []
+        for direction in ((0,) if mirror else (0, 1)):
+            flow = None
+            for level in range(6):
+                y, fup = o.spynet_level_input(pyr[level], flow, n_pairs, B, direction)
+                convs = self.spynet.basic_module[level].basic_module
+                for m in range(4):
+                    y = o.conv2d(y, self._pc(convs[m].conv, tc=False), act=o.ACT_RELU, use_tc=False)
+                flow = o.conv2d(y, self._pc(convs[4].conv, tc=False), epi=o.EPI_RESADD, res=fup, use_tc=False)
+            f = o.flow_resize(flow, Hp, Wp)
+            if self.flow_smooth:
+                f = o.flow_smooth(f, self.region)
+            flows.append(f.view(T - 1, B, Hp, Wp, 2))
+        if mirror:                      # vmg.py:461-462 (smoothing commutes with the temporal flip)
+            flows.append(flows[0].flip(0).contiguous())
+        return flows[0], flows[1]
+
+    # -------------------------------------------------------------------------------------------
+    # TAB (function.py:1212-1217): Morph-FC mixing (function.py:743-805) + conv FFN (function.py:67-79)
+    # -------------------------------------------------------------------------------------------
+    def _tab(self, blk, st, x, B, T):
+        o = _ops
+        N, H, W, C = x.shape
+        sm = blk.spatial_mixing
+        xn = o.layernorm(x, blk.norm2.weight, blk.norm2.bias)
+        branches = []
+        for axis, (lin, gamma, chunk, Cp) in enumerate(((sm.mlp_h[0], sm.gamma_h, sm.chunk_h, sm.Ch),
+                                                        (sm.mlp_w[0], sm.gamma_w, sm.chunk_w, sm.Cw))):
+            o.decay_weights_(lin.weight.data, gamma)                     # function.py:765-768 / 778-781
+            A = o.morph_gather(xn, chunk, axis)
+            Y = o.linear(A, self._pc(lin, force=True), act=o.ACT_RELU, out_scale=1.0 / Cp)
+            branches.append(o.morph_scatter(Y, N, H, W, C, chunk, axis))
+            del A, Y
+        h, w = branches
+        if self.channel_mixer == 'rcab':                                 # function.py:542-583
+            body = sm.mlp_c.body
+            r = o.conv2d(xn, self._pc(body[0]), act=o.ACT_RELU)
+            r = o.conv2d(r, self._pc(body[2]))
+            y = o.channel_sum(r, None, None, 1, N, H * W, 1.0 / (H * W))
+            du = body[3].conv_du
+            y = o.linear(y, self._pc(du[0], tc=False), act=o.ACT_RELU, use_tc=False)
+            y = o.linear(y, self._pc(du[2], tc=False), act=o.ACT_SIGMOID, use_tc=False)
+            c = o.ca_apply(r, xn, y, H * W, 1.0 / C)
+            del r
+        else:
+            c = o.linear(xn, self._pc(sm.mlp_c[0]), act=o.ACT_RELU, out_scale=1.0 / C)
+        a = o.channel_sum(h, w, c, T, B, H * W, 1.0 / (T * H * W))       # function.py:791
+        a = o.linear(a, self._pc(sm.reweight.fc1, tc=False), act=o.ACT_GELU, use_tc=False)
+        a = o.softmax3(o.linear(a, self._pc(sm.reweight.fc2, tc=False), use_tc=False))
+        mix = o.mix3(h, w, c, a, T, B, H * W)
+        del h, w, c, branches
+        x = o.linear(mix, self._pc(sm.proj), epi=o.EPI_GATE, res=x, aux=xn, res_scale=self.m_scaling)
+        del mix, xn
+        xn = o.layernorm(x, blk.norm3.weight, blk.norm3.bias)
+        cm = blk.channel_mixing
+        u = o.conv2d(xn, self._pc(cm.fc1, groups=self.n_groups), act=o.ACT_GELU)
+        x = o.linear(u, self._pc(cm.fc2), epi=o.EPI_RESADD, res=x, res_scale=self.m_scaling)
+        return x
+
+    # -------------------------------------------------------------------------------------------
+    # Trajectory_multi_head (trajectory.py:300-490) + LTAM wins (trajectory.py:672-795)
+    # -------------------------------------------------------------------------------------------
+    def _resblocks(self, rb, srcs, out):
+        o = _ops
+        main = rb.main
+        y = o.conv2d(srcs, self._pc(main[0]), act=o.ACT_LRELU, alpha=0.1)
+        blocks = main[2]
+        nb = len(blocks)
+        if nb == 0:
+            out.copy_(y)
+            return out
+        for k, blk in enumerate(blocks):
+            t = o.conv2d(y, self._pc(blk.conv1), act=o.ACT_RELU)
+            y = o.conv2d(t, self._pc(blk.conv2), epi=o.EPI_RESADD, res=y, res_scale=self.r_scaling,
+                         out=out if k == nb - 1 else None)
+        return y
+
+    def _trajectory(self, st, x, B, T, flows_f, flows_b):
+        o = _ops
+        tm = st.traj_mixing
+        N, H, W, C = x.shape
+        n = B
+        xs = x.view(T, n, H, W, C)
+        qn = o.l2norm(x).view(T, n, H, W, C)            # queries; a key frame's keys are its own qn
+        stride = st.key_stride
+        kcap = (T + stride - 1) // stride
+        frame_elems = n * H * W * C
+        proj = self._pc(tm.LTAM.proj)
+        rel = tm.LTAM.relative_pos_encoding.detach().contiguous()
+        decay = tm.LTAM.decay_v
+        feats = []
+        for order, keyset, flows, fidx, kstep in (
+                (range(T - 1, -1, -1), set(range(T - 1, -1, -stride)), flows_b, (lambda i: i), -stride),
+                (range(0, T), set(range(0, T, stride)), flows_f, (lambda i: i - 1), stride)):
+            fbuf = torch.empty((T, n, H, W, C), device=x.device, dtype=x.dtype)
+            loc = [torch.empty((n, H, W, 2 * kcap), device=x.device, dtype=torch.float32) for _ in range(2)]
+            o.loc_identity_(loc[0], 0)
+            cur_loc, K = 0, 0
+            prev = None
+            first_frame = None
+            for i in order:
+                if prev is None:
+                    first_frame = i
+                    feat_in = torch.zeros((n, H, W, C), device=x.device, dtype=x.dtype)
+                else:
+                    flow = flows[fidx(i)]
+                    warped = o.flow_warp_bilinear(prev, flow)
+                    o.flow_warp_nearest(loc[cur_loc], flow, 2 * K, loc[1 - cur_loc])
+                    cur_loc = 1 - cur_loc
+                    att = o.ltam_wins(qn[i], qn[first_frame], fbuf[first_frame], kstep * frame_elems, K, loc[cur_loc],
+                                      rel, decay, st.heads)
+                    feat_in = o.linear(att, proj, epi=o.EPI_RESADD, res=warped)
+                    if i in keyset:
+                        o.loc_identity_(loc[cur_loc], 2 * K)
+                if i in keyset:
+                    K += 1                              # frame i is pushed as key frame K-1 once fbuf[i] is written
+                prev = self._resblocks(tm.resblocks, (xs[i], feat_in), fbuf[i])
+            feats.append(fbuf)
+        out = o.conv2d((feats[0].view(N, H, W, C), x, feats[1].view(N, H, W, C)), self._pc(tm.fusion),
+                       act=o.ACT_LRELU, alpha=0.1)
+        return out
+
+    # -------------------------------------------------------------------------------------------
+    def _stage(self, st, x, B, T, flows):
+        o = _ops
+        shortcut = x
+        for blk in st.mlp_blocks:
+            x = self._tab(blk, st, x, B, T)
+        if self.local_fuse:                                               # function.py:1503-1505
+            x = o.conv2d(x, self._pc(st.local_cnn), epi=o.EPI_RESADD, res=shortcut)
+        if st.has_traj:
+            x = self._trajectory(st, x, B, T, flows[0], flows[1])
+        return x
+
+    def _resample(self, rs, x, add=None):                                 # layers.py:777-798
+        o = _ops
+        y = o.resample_ln(x, add, rs.norm.weight, rs.norm.bias, up=(rs.mode == 'up'))
+        return o.linear(y, self._pc(rs.linear))
+
+    def _shortcut(self, sc, x):                                           # vmg.py:389-400,519,525
+        o = _ops
+        u = o.maxpool4(x)
+        u = o.linear(u, self._pc(sc[0]))
+        return o.groupnorm1_relu(u, sc[1].weight, sc[1].bias)
+
+    @torch.no_grad()
+    def forward(self, x, flow_pretrained=None, config_amp=None):
+        o = _ops
+        o.require_device()
+        if self.training:
+            raise NotImplementedError('vmg_b200.VMG implements the inference forward only; call .eval()')
+        B, T, Cin, H, W = x.shape
+        assert H >= 64 and W >= 64, 'The height and width must larger than 64.'
+        if T != self.num_out_frames:
+            raise RuntimeError(f'shape mismatch: T={T} but num_out_frames={self.num_out_frames} (models/vmg.py:635)')
+        x = x.contiguous().float()
+        self.frames_mirror = o.mirror_check(x)                            # vmg.py:426-432
+        Hp = int(math.ceil(H / self.scale)) * self.scale
+        Wp = int(math.ceil(W / self.scale)) * self.scale
+        xp = o.pad_input(x, Hp, Wp)                                       # [T*B,Hp,Wp,3] fp32
+        flows = self._compute_flow(xp, B, T, self.frames_mirror)
+        adt = self._adt
+        E, D = self.encoder_layers, self.decoder_layers
+        x0 = o.conv2d(xp, self._pc(self.input_proj.proj[0], tc=False), act=o.ACT_LRELU, alpha=0.01, out_dtype=adt,
+                      use_tc=False)
+        if self.num_layers > 3:                                           # vmg.py:466-567
+            x1 = self._stage(E[0], x0, B, T, flows)
+            x1_3 = self._shortcut(self.sc_64_16, x1) if self.mdsc else None
+            x2 = self._stage(E[1], self._resample(self.downsample[0], x1), B, T, None)
+            x2_4 = self._shortcut(self.sc_32_8, x2) if self.mdsc else None
+            x3 = self._stage(E[2], self._resample(self.downsample[1], x2), B, T, None)
+            x4 = self._stage(E[3], self._resample(self.downsample[2], x3, x1_3), B, T, None)
+            x5 = self._stage(D[0], self._resample(self.upsample[0], x4, x2_4), B, T, None)
+            x6 = self._stage(D[1], self._resample(self.upsample[1], x5, x3), B, T, None)
+            x7 = self._stage(D[2], self._resample(self.upsample[2], x6, x2), B, T, flows)
+            y = o.add(x7, x1)
+        else:                                                             # vmg.py:569-582
+            x1 = self._stage(E[0], x0, B, T, flows)
+            x2 = self._stage(E[1], self._resample(self.downsample[0], x1), B, T, None)
+            x3 = self._stage(D[0], self._resample(self.upsample[0], x2), B, T, flows)
+            y = o.add(x3, x1)
+        if self.local_fuse:                                               # vmg.py:616-617
+            y = o.conv2d(y, self._pc(self.local_cnn), epi=o.EPI_RESADD, res=x0)
+        if Hp != H or Wp != W:
+            y = y[:, :H, :W, :].contiguous()                              # vmg.py:619
+        out = torch.empty((B, T, 3, 4 * H, 4 * W), device=x.device, dtype=torch.float32)
+        C = y.shape[-1]
+        yv = y.view(T, B, H, W, C)
+        tc = max(1, self.recon_chunk // B)
+        for t0 in range(0, T, tc):                                        # vmg.py:629-636
+            z = yv[t0:t0 + tc].reshape(-1, H, W, C)
+            z = o.conv2d(z, self._pc(self.upconv1), act=o.ACT_LRELU, alpha=0.1, pixel_shuffle=2)
+            z = o.conv2d(z, self._pc(self.upconv2), act=o.ACT_LRELU, alpha=0.1, pixel_shuffle=2)
+            z = o.conv2d(z, self._pc(self.HRconv), act=o.ACT_LRELU, alpha=0.1)
+            z = o.conv2d(z, self._pc(self.conv_last), out_dtype=torch.float32)
+            o.final_output(z, x, out, t0)
+        return out

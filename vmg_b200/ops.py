@@ -1,0 +1,470 @@
+"""ctypes binding of libvmgb.so (the C ABI in include/vmgb.h) + thin tensor-level wrappers.
+
+PyTorch is used here for device memory, streams and dtype bookkeeping only: every arithmetic step of
+the VMG forward goes through a vmgb_* kernel.  There is NO fallback: importing works without a GPU
+(so the ABI can be inspected), but any op call without the library or without an sm_100 device raises.
+
+Internal activation layout: channels-last, frames time-major -- tensors are [T*B, H, W, C] (or row
+matrices [rows, C]).  See include/vmgb.h for the per-kernel contracts and reference citations.
+"""
+import ctypes
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'vmgb.h')
+LIB_PATH = os.path.join(_HERE, 'libvmgb.so')
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
+EPI_STORE, EPI_RESADD, EPI_GATE = 0, 1, 2
+
+_CTYPES = {
+    'int': ctypes.c_int, 'float': ctypes.c_float, 'long long': ctypes.c_longlong,
+    'void*': ctypes.c_void_p, 'const void*': ctypes.c_void_p, 'float*': ctypes.c_void_p,
+    'const float*': ctypes.c_void_p, 'const char*': ctypes.c_char_p, 'void': None,
+}
+
+
+def parse_header(path=HEADER):
+    """Returns {symbol: (restype, [argtypes])} for every prototype declared in include/vmgb.h."""
+    src = open(path).read()
+    src = re.sub(r'/\*.*?\*/', ' ', src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r'\b(int|long long|const char\*)\s+(vmgb_\w+)\s*\(([^)]*)\)\s*;', src):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        argt = []
+        if args and args != 'void':
+            for a in args.split(','):
+                a = ' '.join(a.split())
+                t = re.sub(r'\s*\w+$', '', a).replace(' *', '*')
+                argt.append(_CTYPES[t])
+        protos[name] = (_CTYPES[ret], argt)
+    return protos
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} is missing: build it with vmg_b200/csrc/build.sh '
+                               '(python -c "import __graft_entry__ as g; g.build()"). There is no fallback path.')
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (ret, argt) in parse_header().items():
+            fn = getattr(L, name)
+            fn.restype = ret
+            fn.argtypes = argt
+        _lib = L
+    return _lib
+
+
+_checked = False
+
+
+def require_device():
+    global _checked
+    if _checked:
+        return
+    if not torch.cuda.is_available():
+        raise RuntimeError('vmg_b200 needs a CUDA device (sm_100a); there is no CPU fallback.')
+    rc = lib().vmgb_device_check()
+    if rc != 0:
+        raise RuntimeError(f'vmg_b200 kernels are sm_100a-only; vmgb_device_check() = {rc}')
+    _checked = True
+
+
+def _ck(rc, name):
+    if rc != 0:
+        msg = ''
+        if rc == -3:
+            msg = ' cuda: ' + (lib().vmgb_last_cuda_error_string() or b'').decode()
+        raise RuntimeError(f'{name} failed with code {rc}.{msg}')
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f'unsupported dtype {t.dtype}')
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _pix(t):
+    """(ptr, pitch) of a channels-last tensor whose pixels are uniformly strided (slices of a wider
+    contiguous buffer along the channel dim are allowed)."""
+    assert t.stride(-1) == 1, 'channel dim must be contiguous'
+    pitch = t.stride(-2) if t.dim() >= 2 else t.shape[-1]
+    exp = pitch
+    for d in range(t.dim() - 2, -1, -1):
+        if t.shape[d] != 1:
+            assert t.stride(d) == exp, f'non-uniform pixel stride {t.stride()} for shape {tuple(t.shape)}'
+        exp *= t.shape[d]
+    return t.data_ptr(), pitch
+
+
+def launch_count():
+    return int(lib().vmgb_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------
+# weights
+# ---------------------------------------------------------------------------------------------
+class PackedConv:
+    """Kernel-side copy of one Conv2d / Linear weight (fp32 [G][taps][Cin_g][Cout_g] and, for the
+    tcgen05 path, bf16 [G][taps][Cout_g][Kp])."""
+    __slots__ = ('w32', 'wtc', 'Kp', 'bias', 'Cout', 'Cin', 'R', 'S', 'groups')
+
+
+def pack_conv(weight, bias, groups=1, tc=False):
+    require_device()
+    w = weight.detach()
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    w = w.contiguous().float()
+    Cout, Cin_g, R, S = w.shape
+    pc = PackedConv()
+    pc.Cout, pc.Cin, pc.R, pc.S, pc.groups = Cout, Cin_g * groups, R, S, groups
+    pc.bias = bias.detach().contiguous().float() if bias is not None else None
+    pc.w32 = torch.empty(groups * R * S * Cin_g * (Cout // groups), device=w.device, dtype=torch.float32)
+    _ck(lib().vmgb_pack_weight(w.data_ptr(), pc.w32.data_ptr(), Cout, Cin_g, R, S, groups, _stream()), 'vmgb_pack_weight')
+    pc.wtc, pc.Kp = None, 0
+    if tc:
+        pc.Kp = (Cin_g + 15) // 16 * 16
+        pc.wtc = torch.empty(groups * R * S * (Cout // groups) * pc.Kp, device=w.device, dtype=torch.bfloat16)
+        _ck(lib().vmgb_pack_weight_tc(w.data_ptr(), pc.wtc.data_ptr(), Cout, Cin_g, pc.Kp, R, S, groups, _stream()),
+            'vmgb_pack_weight_tc')
+    return pc
+
+
+def tc_supported(pc, xs, n_src):
+    """Shapes the tcgen05 kernel takes (see csrc/conv_tc.cu)."""
+    if pc.wtc is None or xs[0].dtype != torch.bfloat16:
+        return False
+    cin_g = pc.Cin // pc.groups
+    if n_src > 1 and (pc.Cin // n_src) % 16:
+        return False
+    if pc.groups > 1 and cin_g % 4:
+        return False
+    return (pc.Cout // pc.groups) >= 8 and all(_pix(x)[1] % 8 == 0 and x.data_ptr() % 16 == 0 for x in xs) and cin_g >= 16
+
+
+def conv2d(x, pc, act=ACT_NONE, alpha=0.0, out_scale=1.0, epi=EPI_STORE, res=None, res_scale=1.0, aux=None,
+           pixel_shuffle=0, out=None, out_dtype=None, use_tc=True, tc_variant=0):
+    """x: [N,H,W,Cin] tensor or tuple of up to 3 equally wide tensors (virtual concat).  Returns
+    [N,H,W,Cout] (or [N,2H,2W,Cout/4] with pixel_shuffle=2)."""
+    require_device()
+    xs = x if isinstance(x, (tuple, list)) else (x,)
+    n_src = len(xs)
+    N, H, W, _ = xs[0].shape
+    ptrs = [_pix(t) for t in xs]
+    for t, (p, pitch) in zip(xs, ptrs):
+        assert t.shape == xs[0].shape and t.dtype == xs[0].dtype and pitch == ptrs[0][1]
+    assert xs[0].shape[-1] * n_src == pc.Cin, (xs[0].shape, n_src, pc.Cin)
+    if out is None:
+        shape = (N, 2 * H, 2 * W, pc.Cout // 4) if pixel_shuffle == 2 else (N, H, W, pc.Cout)
+        out = torch.empty(shape, device=xs[0].device, dtype=out_dtype or xs[0].dtype)
+    optr, opitch = _pix(out)
+    rptr, rpitch, rdt = (None, 0, 0)
+    if res is not None:
+        rptr, rpitch = _pix(res)
+        rdt = _dt(res)
+        assert res.shape == out.shape
+    aptr, apitch, adt = (None, 0, 0)
+    if aux is not None:
+        aptr, apitch = _pix(aux)
+        adt = _dt(aux)
+        assert aux.shape == out.shape
+    p1 = ptrs[1][0] if n_src > 1 else None
+    p2 = ptrs[2][0] if n_src > 2 else None
+    bias = _ptr(pc.bias)
+    if use_tc and tc_supported(pc, xs, n_src):
+        _ck(lib().vmgb_conv2d_nhwc_tc(ptrs[0][0], p1, p2, n_src, ptrs[0][1], pc.wtc.data_ptr(), pc.Kp, bias,
+                                      optr, _dt(out), opitch, rptr, rdt, rpitch, aptr, adt, apitch,
+                                      N, H, W, pc.Cin, pc.Cout, pc.R, pc.S, pc.groups,
+                                      act, alpha, out_scale, epi, res_scale, pixel_shuffle, tc_variant, _stream()),
+            'vmgb_conv2d_nhwc_tc')
+    else:
+        _ck(lib().vmgb_conv2d_nhwc(ptrs[0][0], p1, p2, n_src, _dt(xs[0]), ptrs[0][1], pc.w32.data_ptr(), bias,
+                                   optr, _dt(out), opitch, rptr, rdt, rpitch, aptr, adt, apitch,
+                                   N, H, W, pc.Cin, pc.Cout, pc.R, pc.S, pc.groups,
+                                   act, alpha, out_scale, epi, res_scale, pixel_shuffle, _stream()),
+            'vmgb_conv2d_nhwc')
+    return out
+
+
+def linear(x, pc, **kw):
+    """x [..., K] -> [..., N]; a Linear is the 1x1 'conv' over a [1,1,rows,K] image."""
+    lead = x.shape[:-1]
+    rows = 1
+    for s in lead:
+        rows *= s
+    xv = x.reshape(1, 1, rows, x.shape[-1])
+    for k in ('res', 'aux', 'out'):
+        if kw.get(k) is not None:
+            kw[k] = kw[k].reshape(1, 1, rows, kw[k].shape[-1])
+    y = conv2d(xv, pc, **kw)
+    return y.reshape(*lead, pc.Cout)
+
+
+# ---------------------------------------------------------------------------------------------
+# row kernels
+# ---------------------------------------------------------------------------------------------
+def layernorm(x, gamma, beta, out_dtype=None, eps=1e-5):
+    require_device()
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype or x.dtype)
+    _ck(lib().vmgb_layernorm(x.data_ptr(), _dt(x), out.data_ptr(), _dt(out), gamma.data_ptr(), beta.data_ptr(),
+                             x.numel() // C, C, eps, _stream()), 'vmgb_layernorm')
+    return out
+
+
+def l2norm(x, out_dtype=None):
+    require_device()
+    ptr, pitch = _pix(x)
+    C = x.shape[-1]
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype or x.dtype)
+    _ck(lib().vmgb_l2norm(ptr, _dt(x), pitch, out.data_ptr(), _dt(out), x.numel() // C, C, _stream()), 'vmgb_l2norm')
+    return out
+
+
+def morph_gather(x, chunk, axis):
+    require_device()
+    N, H, W, C = x.shape
+    assert x.is_contiguous()
+    Cp = -(-C // chunk) * chunk
+    L, O = (H, W) if axis == 0 else (W, H)
+    rows = N * (-(-L // chunk) * chunk) * O
+    A = torch.empty((rows, Cp), device=x.device, dtype=x.dtype)
+    _ck(lib().vmgb_morph_permute(x.data_ptr(), _dt(x), A.data_ptr(), _dt(A), N, H, W, C, chunk, axis, 0, _stream()),
+        'vmgb_morph_permute')
+    return A
+
+
+def morph_scatter(Y, N, H, W, C, chunk, axis):
+    require_device()
+    assert Y.is_contiguous()
+    out = torch.empty((N, H, W, C), device=Y.device, dtype=Y.dtype)
+    _ck(lib().vmgb_morph_permute(Y.data_ptr(), _dt(Y), out.data_ptr(), _dt(out), N, H, W, C, chunk, axis, 1, _stream()),
+        'vmgb_morph_permute')
+    return out
+
+
+def channel_sum(a, b, c, n_seg, groups, seg_rows, scale):
+    require_device()
+    C = a.shape[-1]
+    for t in (a, b, c):
+        assert t is None or (t.is_contiguous() and t.dtype == a.dtype)
+    out = torch.zeros((groups, C), device=a.device, dtype=torch.float32)
+    _ck(lib().vmgb_channel_sum(a.data_ptr(), _ptr(b), _ptr(c), _dt(a), out.data_ptr(), n_seg, groups, seg_rows, C,
+                               scale, _stream()), 'vmgb_channel_sum')
+    return out
+
+
+def softmax3(logits):
+    require_device()
+    B, C3 = logits.shape
+    assert logits.dtype == torch.float32 and logits.is_contiguous()
+    a = torch.empty((B, 3, C3 // 3), device=logits.device, dtype=torch.float32)
+    _ck(lib().vmgb_softmax3(logits.data_ptr(), a.data_ptr(), B, C3 // 3, _stream()), 'vmgb_softmax3')
+    return a
+
+
+def mix3(h, w, c, a, n_seg, B, seg_rows):
+    require_device()
+    C = h.shape[-1]
+    out = torch.empty_like(h)
+    _ck(lib().vmgb_mix3(h.data_ptr(), w.data_ptr(), c.data_ptr(), _dt(h), a.data_ptr(), out.data_ptr(), _dt(out),
+                        n_seg, B, seg_rows, C, _stream()), 'vmgb_mix3')
+    return out
+
+
+def ca_apply(u, x, y, rows_per_frame, scale):
+    require_device()
+    C = u.shape[-1]
+    frames = u.numel() // C // rows_per_frame
+    out = torch.empty_like(u)
+    _ck(lib().vmgb_ca_apply(u.data_ptr(), x.data_ptr(), _dt(u), y.data_ptr(), out.data_ptr(), _dt(out), frames,
+                            rows_per_frame, C, scale, _stream()), 'vmgb_ca_apply')
+    return out
+
+
+def add(a, b):
+    require_device()
+    assert a.shape == b.shape and a.dtype == b.dtype and a.is_contiguous() and b.is_contiguous()
+    out = torch.empty_like(a)
+    _ck(lib().vmgb_add(a.data_ptr(), b.data_ptr(), _dt(a), out.data_ptr(), _dt(out), a.numel(), _stream()), 'vmgb_add')
+    return out
+
+
+def decay_weights_(w, gamma):
+    require_device()
+    assert w.dtype == torch.float32 and gamma.dtype == torch.float32 and w.is_contiguous() and gamma.is_contiguous()
+    assert w.shape == gamma.shape
+    _ck(lib().vmgb_decay_weights(w.data_ptr(), gamma.data_ptr(), w.numel(), _stream()), 'vmgb_decay_weights')
+    return w
+
+
+def resample_ln(x, add_, gamma, beta, up, eps=1e-5):
+    require_device()
+    N, H, W, C = x.shape
+    assert x.is_contiguous() and (add_ is None or (add_.is_contiguous() and add_.shape == x.shape))
+    shape = (N, 2 * H, 2 * W, C // 4) if up else (N, H // 2, W // 2, 4 * C)
+    out = torch.empty(shape, device=x.device, dtype=x.dtype)
+    _ck(lib().vmgb_resample_ln(x.data_ptr(), _ptr(add_), _dt(x), out.data_ptr(), _dt(out), gamma.data_ptr(),
+                               beta.data_ptr(), N, H, W, C, int(up), eps, _stream()), 'vmgb_resample_ln')
+    return out
+
+
+def maxpool4(x):
+    require_device()
+    N, H, W, C = x.shape
+    out = torch.empty((N, H // 4, W // 4, C), device=x.device, dtype=x.dtype)
+    _ck(lib().vmgb_maxpool4(x.data_ptr(), _dt(x), out.data_ptr(), _dt(out), N, H, W, C, _stream()), 'vmgb_maxpool4')
+    return out
+
+
+def groupnorm1_relu(x, gamma, beta, eps=1e-5):
+    """GroupNorm(1, C) per frame followed by ReLU; x [N,H,W,C]."""
+    require_device()
+    N, H, W, C = x.shape
+    stats = torch.zeros((N, 2), device=x.device, dtype=torch.float32)
+    _ck(lib().vmgb_frame_stats(x.data_ptr(), _dt(x), stats.data_ptr(), N, H * W * C, _stream()), 'vmgb_frame_stats')
+    out = torch.empty_like(x)
+    _ck(lib().vmgb_groupnorm1_relu(x.data_ptr(), _dt(x), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                   out.data_ptr(), _dt(out), N, H * W, C, eps, _stream()), 'vmgb_groupnorm1_relu')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# warps / trajectory
+# ---------------------------------------------------------------------------------------------
+def flow_warp_bilinear(x, flow, out=None):
+    require_device()
+    n, h, w, C = x.shape
+    xp, xpitch = _pix(x)
+    if out is None:
+        out = torch.empty((n, h, w, C), device=x.device, dtype=x.dtype)
+    op, opitch = _pix(out)
+    assert flow.dtype == torch.float32 and flow.is_contiguous() and flow.shape == (n, h, w, 2)
+    _ck(lib().vmgb_flow_warp_bilinear(xp, _dt(x), xpitch, flow.data_ptr(), op, _dt(out), opitch, n, h, w, C, _stream()),
+        'vmgb_flow_warp_bilinear')
+    return out
+
+
+def flow_warp_nearest(loc, flow, K2, out):
+    require_device()
+    n, h, w, pitch = loc.shape
+    assert loc.is_contiguous() and out.is_contiguous() and out.shape == loc.shape and loc.dtype == torch.float32
+    _ck(lib().vmgb_flow_warp_nearest(loc.data_ptr(), pitch, flow.data_ptr(), out.data_ptr(), pitch, n, h, w, K2,
+                                     _stream()), 'vmgb_flow_warp_nearest')
+    return out
+
+
+def loc_identity_(loc, c0):
+    require_device()
+    n, h, w, pitch = loc.shape
+    _ck(lib().vmgb_loc_identity(loc.data_ptr(), pitch, c0, n, h, w, _stream()), 'vmgb_loc_identity')
+    return loc
+
+
+def flow_smooth(flow, r):
+    require_device()
+    n, h, w, _ = flow.shape
+    out = torch.empty_like(flow)
+    _ck(lib().vmgb_flow_smooth(flow.data_ptr(), out.data_ptr(), n, h, w, r, _stream()), 'vmgb_flow_smooth')
+    return out
+
+
+def ltam_wins(q, keys0, vals0, kv_stride, K, loc, rel, decay, heads):
+    """keys0 / vals0: tensors whose data_ptr is key-frame 0; key-frame k lives kv_stride elements later."""
+    require_device()
+    n, h, w, C = q.shape
+    assert q.is_contiguous() and keys0.dtype == q.dtype and vals0.dtype == q.dtype
+    out = torch.empty_like(q)
+    _ck(lib().vmgb_ltam_wins(q.data_ptr(), keys0.data_ptr(), vals0.data_ptr(), _dt(q), kv_stride, loc.data_ptr(),
+                             loc.shape[-1], rel.data_ptr(), decay.data_ptr(), out.data_ptr(), _dt(out), n, h, w, C,
+                             heads, K, _stream()), 'vmgb_ltam_wins')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# SPyNet helpers, input / output
+# ---------------------------------------------------------------------------------------------
+def spynet_prep(frames, mean, std, h_up, w_up):
+    require_device()
+    n, H, W, _ = frames.shape
+    out = torch.empty((n, h_up, w_up, 3), device=frames.device, dtype=torch.float32)
+    _ck(lib().vmgb_spynet_prep(frames.data_ptr(), out.data_ptr(), *mean, *std, n, H, W, h_up, w_up, _stream()),
+        'vmgb_spynet_prep')
+    return out
+
+
+def avgpool2(x):
+    require_device()
+    n, H, W, C = x.shape
+    out = torch.empty((n, H // 2, W // 2, C), device=x.device, dtype=torch.float32)
+    _ck(lib().vmgb_avgpool2(x.data_ptr(), out.data_ptr(), n, H, W, C, _stream()), 'vmgb_avgpool2')
+    return out
+
+
+def spynet_level_input(pyr, flow_coarse, n_pairs, B, direction):
+    require_device()
+    _, h, w, _ = pyr.shape
+    out8 = torch.empty((n_pairs, h, w, 8), device=pyr.device, dtype=torch.float32)
+    fup = torch.empty((n_pairs, h, w, 2), device=pyr.device, dtype=torch.float32)
+    _ck(lib().vmgb_spynet_level_input(pyr.data_ptr(), _ptr(flow_coarse), out8.data_ptr(), fup.data_ptr(), n_pairs, B,
+                                      direction, h, w, _stream()), 'vmgb_spynet_level_input')
+    return out8, fup
+
+
+def flow_resize(flow, h, w):
+    require_device()
+    n, hu, wu, _ = flow.shape
+    out = torch.empty((n, h, w, 2), device=flow.device, dtype=torch.float32)
+    _ck(lib().vmgb_flow_resize(flow.data_ptr(), out.data_ptr(), n, hu, wu, h, w, _stream()), 'vmgb_flow_resize')
+    return out
+
+
+def pad_input(x, Hp, Wp):
+    """x [B,T,3,H,W] fp32 -> time-major channels-last [T*B,Hp,Wp,3]."""
+    require_device()
+    B, T, _, H, W = x.shape
+    out = torch.empty((T * B, Hp, Wp, 3), device=x.device, dtype=torch.float32)
+    _ck(lib().vmgb_pad_input(x.data_ptr(), out.data_ptr(), B, T, H, W, Hp, Wp, _stream()), 'vmgb_pad_input')
+    return out
+
+
+def mirror_check(x):
+    """vmg.py:426-432 -- True iff the clip is a palindrome (host sync, even T only)."""
+    require_device()
+    B, T = x.shape[:2]
+    if T % 2:
+        return False
+    s = torch.zeros(1, device=x.device, dtype=torch.float32)
+    _ck(lib().vmgb_mirror_check(x.data_ptr(), s.data_ptr(), B, T, x[0, 0].numel(), _stream()), 'vmgb_mirror_check')
+    return bool(s.item() == 0.0)
+
+
+def final_output(y, x, out, t0):
+    """y [Tc*B,4H,4W,3] (time-major chunk starting at frame t0) ; x [B,T,3,H,W] ; out [B,T,3,4H,4W]."""
+    require_device()
+    B, T, _, H, W = x.shape
+    Tc = y.shape[0] // B
+    yp, ypitch = _pix(y)
+    _ck(lib().vmgb_final_output(yp, _dt(y), ypitch, x.data_ptr(), out.data_ptr(), B, T, t0, Tc, H, W, _stream()),
+        'vmgb_final_output')
+    return out
