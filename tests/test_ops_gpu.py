@@ -1,0 +1,212 @@
+"""`-m gpu`: every CUDA kernel of libvmgb (called through the C ABI via vmg_b200/ops.py) against the plain
+PyTorch fp32 reference of the same op (tests/emu_ops.py), on seeded inputs, incl. ragged / edge shapes."""
+import pytest
+import torch
+
+from tests import emu_ops as emu
+from vmg_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(*shape, generator=g) * 2 - 1) * scale
+
+
+def close(a, b, tol):
+    a, b = a.float().cpu(), b.float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    assert err <= tol, f'max-abs {err} > {tol}'
+
+
+def conv_case(N, H, W, Cin, Cout, R, groups, dtype, tc, n_src=1, act=ops.ACT_NONE, epi=ops.EPI_STORE, ps=0, seed=0, out_dtype=None):
+    w = rnd(Cout, Cin // groups, R, R, seed=seed + 1, scale=(Cin // groups * R * R) ** -0.5)
+    b = rnd(Cout, seed=seed + 2, scale=0.5)
+    xs = [rnd(N, H, W, Cin // n_src, seed=seed + 10 + i) for i in range(n_src)]
+    if dtype == torch.bfloat16:
+        xs = [x.bfloat16() for x in xs]
+        w = w.bfloat16().float()
+    oshape = (N, 2 * H, 2 * W, Cout // 4) if ps else (N, H, W, Cout)
+    res = rnd(*oshape, seed=seed + 3).to(dtype) if epi != ops.EPI_STORE else None
+    aux = rnd(*oshape, seed=seed + 4).to(dtype) if epi == ops.EPI_GATE else None
+    kw = dict(act=act, alpha=0.1, out_scale=0.5, epi=epi, res_scale=0.7, pixel_shuffle=ps, out_dtype=out_dtype)
+    ref = emu.conv2d(tuple(xs) if n_src > 1 else xs[0], emu.pack_conv(w, b, groups), res=res, aux=aux, **kw)
+    pc = ops.pack_conv(w.to(DEV), b.to(DEV), groups, tc=tc)
+    dx = tuple(x.to(DEV) for x in xs) if n_src > 1 else xs[0].to(DEV)
+    out = ops.conv2d(dx, pc, res=None if res is None else res.to(DEV), aux=None if aux is None else aux.to(DEV), use_tc=tc, **kw)
+    torch.cuda.synchronize()
+    return out, ref
+
+
+GENERIC = [
+    (2, 9, 11, 3, 24, 3, 1, ops.ACT_LRELU, ops.EPI_STORE, 0, 1),     # input_proj-like, ragged
+    (1, 16, 16, 144, 144, 3, 1, ops.ACT_RELU, ops.EPI_RESADD, 0, 1),
+    (1, 12, 20, 112, 672, 3, 4, ops.ACT_GELU, ops.EPI_STORE, 0, 1),  # grouped FFN fc1
+    (3, 8, 8, 8, 32, 7, 1, ops.ACT_RELU, ops.EPI_STORE, 0, 1),       # SPyNet 7x7
+    (1, 8, 8, 16, 2, 7, 1, ops.ACT_NONE, ops.EPI_RESADD, 0, 1),      # SPyNet last conv, Cout=2
+    (1, 1, 300, 228, 228, 1, 1, ops.ACT_RELU, ops.EPI_STORE, 0, 1),  # Morph-FC linear (padded 228)
+    (1, 1, 257, 112, 112, 1, 1, ops.ACT_NONE, ops.EPI_GATE, 0, 1),   # proj + gate
+    (2, 6, 10, 64, 256, 3, 1, ops.ACT_LRELU, ops.EPI_STORE, 2, 1),   # upconv + pixel shuffle
+    (1, 10, 12, 288, 144, 3, 1, ops.ACT_LRELU, ops.EPI_STORE, 0, 2), # resblocks input conv (virtual concat of 2)
+    (1, 7, 9, 336, 112, 1, 1, ops.ACT_LRELU, ops.EPI_STORE, 0, 3),   # trajectory fusion (virtual concat of 3)
+    (1, 20, 20, 64, 3, 3, 1, ops.ACT_NONE, ops.EPI_STORE, 0, 1),     # conv_last
+]
+
+
+@pytest.mark.parametrize('case', GENERIC, ids=lambda c: 'x'.join(map(str, c)))
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['f32', 'bf16'])
+def test_conv_generic(case, dtype):
+    N, H, W, Cin, Cout, R, groups, act, epi, ps, n_src = case
+    out, ref = conv_case(N, H, W, Cin, Cout, R, groups, dtype, False, n_src, act, epi, ps)
+    close(out, ref, 2e-5 if dtype == torch.float32 else 1.5e-2)
+
+
+TC = [c for c in GENERIC if c[3] >= 16] + [
+    (2, 24, 40, 144, 144, 3, 1, ops.ACT_RELU, ops.EPI_STORE, 0, 1),
+    (1, 23, 37, 112, 112, 3, 1, ops.ACT_NONE, ops.EPI_RESADD, 0, 1),   # ragged tile edges
+    (1, 8, 8, 448, 448, 1, 1, ops.ACT_RELU, ops.EPI_STORE, 0, 1),      # W=8 tile shape, N split in 2
+    (1, 1, 1000, 1344, 224, 1, 1, ops.ACT_NONE, ops.EPI_RESADD, 0, 1), # FFN fc2, long K
+    (1, 16, 16, 224, 1344, 3, 4, ops.ACT_GELU, ops.EPI_STORE, 0, 1),   # grouped, Cout_g=336 (2 N tiles of 176)
+    (1, 1, 130, 896, 224, 1, 1, ops.ACT_NONE, ops.EPI_STORE, 0, 1),    # downsample linear
+    (1, 1, 130, 36, 144, 1, 1, ops.ACT_NONE, ops.EPI_STORE, 0, 1),     # upsample linear, K=36 (pitch not 16B multiple -> generic)
+    (4, 16, 16, 144, 576, 3, 1, ops.ACT_LRELU, ops.EPI_STORE, 2, 1),   # upconv1 + PS, 3 N tiles
+]
+
+
+@pytest.mark.parametrize('case', TC, ids=lambda c: 'x'.join(map(str, c)))
+def test_conv_tcgen05(case):
+    N, H, W, Cin, Cout, R, groups, act, epi, ps, n_src = case
+    out, ref = conv_case(N, H, W, Cin, Cout, R, groups, torch.bfloat16, True, n_src, act, epi, ps, out_dtype=torch.float32)
+    close(out, ref, 2e-3)
+
+
+def test_conv_tcgen05_many_tiles_persistent():
+    # more tiles than SMs -> exercises the smem ring wrap-around and both TMEM accumulators
+    out, ref = conv_case(6, 64, 64, 144, 144, 3, 1, torch.bfloat16, True, 1, ops.ACT_RELU, ops.EPI_RESADD, 0, out_dtype=torch.float32)
+    close(out, ref, 2e-3)
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)], ids=['f32', 'bf16'])
+def test_row_kernels(dtype, tol):
+    x = rnd(5, 13, 144, seed=1).to(dtype)
+    g, b = rnd(144, seed=2), rnd(144, seed=3)
+    close(ops.layernorm(x.to(DEV), g.to(DEV), b.to(DEV)), emu.layernorm(x, g, b), tol)
+    close(ops.l2norm(x.to(DEV)), emu.l2norm(x), tol)
+    x4 = rnd(3, 10, 14, 112, seed=4).to(dtype)
+    for axis, chunk in ((0, 8), (1, 16), (0, 12), (1, 12)):
+        A = ops.morph_gather(x4.to(DEV), chunk, axis)
+        close(A, emu.morph_gather(x4, chunk, axis), 0)
+        close(ops.morph_scatter(A, 3, 10, 14, 112, chunk, axis), x4, 0)     # permutation round trip
+    h, w, c = (rnd(6, 8, 9, 112, seed=s).to(dtype) for s in (5, 6, 7))
+    a = ops.channel_sum(h.to(DEV), w.to(DEV), c.to(DEV), 3, 2, 72, 1.0 / 216)
+    a_ref = emu.channel_sum(h, w, c, 3, 2, 72, 1.0 / 216)
+    close(a, a_ref, 1e-5)
+    close(ops.channel_sum(h.to(DEV), None, None, 1, 6, 72, 1.0 / 72), emu.channel_sum(h, None, None, 1, 6, 72, 1.0 / 72), 1e-5)
+    lg = rnd(2, 336, seed=8)
+    s3 = ops.softmax3(lg.to(DEV))
+    close(s3, emu.softmax3(lg), 1e-6)
+    close(ops.mix3(h.to(DEV), w.to(DEV), c.to(DEV), s3, 3, 2, 72), emu.mix3(h, w, c, emu.softmax3(lg), 3, 2, 72), tol)
+    y = torch.sigmoid(rnd(6, 112, seed=9))
+    close(ops.ca_apply(h.to(DEV), w.to(DEV), y.to(DEV), 72, 1 / 112), emu.ca_apply(h, w, y, 72, 1 / 112), tol)
+    close(ops.add(h.to(DEV), w.to(DEV)), emu.add(h, w), tol)
+    wt, gm = rnd(228, 228, seed=10), torch.rand(228, 228) * 0.05 + 0.94
+    close(ops.decay_weights_(wt.clone().to(DEV), gm.to(DEV)), wt * gm, 0)
+    xr = rnd(2, 8, 12, 112, seed=11).to(dtype)
+    ad = rnd(2, 8, 12, 112, seed=12).to(dtype)
+    for up, F_ in ((0, 448), (1, 28)):
+        gg, bb = rnd(F_, seed=13), rnd(F_, seed=14)
+        close(ops.resample_ln(xr.to(DEV), ad.to(DEV), gg.to(DEV), bb.to(DEV), up), emu.resample_ln(xr, ad, gg, bb, up), tol * 2)
+        close(ops.resample_ln(xr.to(DEV), None, gg.to(DEV), bb.to(DEV), up), emu.resample_ln(xr, None, gg, bb, up), tol * 2)
+    close(ops.maxpool4(xr.to(DEV)), emu.maxpool4(xr), 0)
+    close(ops.groupnorm1_relu(xr.to(DEV), g[:112].to(DEV), b[:112].to(DEV)), emu.groupnorm1_relu(xr, g[:112], b[:112]), tol)
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)], ids=['f32', 'bf16'])
+def test_flow_warps(dtype, tol):
+    n, h, w, C = 2, 18, 22, 112
+    x = rnd(n, h, w, C, seed=1).to(dtype)
+    flow = rnd(n, h, w, 2, seed=2, scale=6.0)
+    flow[0, :3, :3] = 0.0
+    flow[0, 5, 5] = torch.tensor([0.5, -0.5])      # exact ties
+    close(ops.flow_warp_bilinear(x.to(DEV), flow.to(DEV)), emu.flow_warp_bilinear(x, flow), tol)
+    K2 = 6
+    loc = torch.zeros(n, h, w, 10)
+    for k in range(3):
+        emu.loc_identity_(loc, 2 * k)
+    dloc = torch.zeros(n, h, w, 10, device=DEV)
+    for k in range(3):
+        ops.loc_identity_(dloc, 2 * k)
+    close(dloc, loc, 0)
+    fl = flow.clone()
+    fl[0, 5, 5] = torch.tensor([1.25, -2.75])
+    o_d = ops.flow_warp_nearest(dloc, fl.to(DEV), K2, torch.zeros_like(dloc))
+    o_r = emu.flow_warp_nearest(loc, fl, K2, torch.zeros_like(loc))
+    mism = ((o_d.cpu()[..., :K2] - o_r[..., :K2]).abs() > 0).float().mean().item()
+    assert mism <= 2e-3, f'nearest-warp mismatch fraction {mism}'   # 1-ulp coordinate ties only
+    close(ops.flow_smooth(flow.to(DEV), 4), emu.flow_smooth(flow, 4), 1e-5)
+
+
+@pytest.mark.parametrize('C,dtype,tol', [(112, torch.float32, 2e-5), (144, torch.float32, 2e-5), (144, torch.bfloat16, 2e-2)])
+def test_ltam_wins(C, dtype, tol):
+    n, h, w, heads, T, stride = 2, 12, 16, 4, 9, 3
+    feats = rnd(T, n, h, w, C, seed=1).to(dtype)
+    keys = emu.l2norm(rnd(T, n, h, w, C, seed=2)).to(dtype)
+    rel = rnd(heads, 4, 4, seed=3, scale=0.05)
+    decay = 1 - 2 ** (-5 - torch.arange(heads - 1, -1, -1, dtype=torch.float32))
+    fe = n * h * w * C
+    dk, dv = keys.to(DEV), feats.to(DEV)
+    for first, kstep, K in ((0, stride, 3), (T - 1, -stride, 2), (0, stride, 1)):
+        g = torch.Generator().manual_seed(7)
+        loc = torch.zeros(n, h, w, 8)
+        loc[..., 0:2 * K:2] = torch.randint(0, w, (n, h, w, K), generator=g).float()
+        loc[..., 1:2 * K:2] = torch.randint(0, h, (n, h, w, K), generator=g).float()
+        q = keys[4]
+        ref = emu.ltam_wins(q, keys[first], feats[first], kstep * fe, K, loc, rel, decay, heads)
+        out = ops.ltam_wins(dk[4], dk[first], dv[first], kstep * fe, K, loc.to(DEV), rel.to(DEV), decay.to(DEV), heads)
+        close(out, ref, tol)
+
+
+def test_spynet_helpers_and_io():
+    B, T, H, W = 2, 3, 66, 70
+    x = torch.rand(B, T, 3, H, W, generator=torch.Generator().manual_seed(1))
+    Hp, Wp = 72, 72
+    xp = ops.pad_input(x.to(DEV), Hp, Wp)
+    close(xp, emu.pad_input(x, Hp, Wp), 0)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    p0 = ops.spynet_prep(xp, mean, std, 96, 96)
+    r0 = emu.spynet_prep(emu.pad_input(x, Hp, Wp), mean, std, 96, 96)
+    close(p0, r0, 2e-5)
+    close(ops.avgpool2(p0), emu.avgpool2(r0), 1e-6)
+    fc = rnd((T - 1) * B, 48, 48, 2, seed=3, scale=3.0)
+    for direction in (0, 1):
+        o8, fu = ops.spynet_level_input(p0, fc.to(DEV), (T - 1) * B, B, direction)
+        r8, ru = emu.spynet_level_input(r0, fc, (T - 1) * B, B, direction)
+        close(fu, ru, 2e-5)
+        close(o8, r8, 1e-4)
+    o8, fu = ops.spynet_level_input(p0, None, (T - 1) * B, B, 0)
+    r8, ru = emu.spynet_level_input(r0, None, (T - 1) * B, B, 0)
+    close(o8, r8, 1e-5)
+    close(ops.flow_resize(fc.to(DEV), 40, 44), emu.flow_resize(fc, 40, 44), 2e-5)
+    assert ops.mirror_check(x.to(DEV)) is False
+    xm = torch.cat([x[:, :1], x[:, :1]], 1)
+    assert ops.mirror_check(xm.to(DEV)) is True
+    y = rnd(2 * B, 4 * H, 4 * W, 3, seed=5)
+    out_d = torch.zeros(B, T, 3, 4 * H, 4 * W, device=DEV)
+    out_r = torch.zeros(B, T, 3, 4 * H, 4 * W)
+    ops.final_output(y.to(DEV), x.to(DEV), out_d, 1)
+    emu.final_output(y, x, out_r, 1)
+    close(out_d, out_r, 2e-6)
+
+
+def test_error_codes():
+    L = ops.lib()
+    assert L.vmgb_layernorm(None, 0, None, 0, None, None, 1, 8, 1e-5, None) == -1
+    x = torch.zeros(1, 4, 4, 16, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.maxpool4(torch.zeros(1, 5, 4, 16, device=DEV))
+    with pytest.raises(RuntimeError):
+        ops.ltam_wins(x, x, x, 0, 1, torch.zeros(1, 4, 4, 2, device=DEV), torch.zeros(3, 4, 4, device=DEV),
+                      torch.zeros(3, device=DEV), 3)

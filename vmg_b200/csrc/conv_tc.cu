@@ -1,0 +1,389 @@
+// conv_tc.cu -- tcgen05 / TMEM / TMA implicit-GEMM convolution and linear (bf16 x bf16 -> fp32) with the
+// fused epilogue menu.  One persistent, warp-specialised kernel:
+//
+//   warp 0 (1 lane)  TMA producer : per K block one 4-D box of the activation tensor (the shifted
+//                                   128-pixel tile of one tap; TMA zero-fills the conv padding and the
+//                                   channel tail) + one 2-D box of the packed weights -> smem ring
+//   warp 1 (1 lane)  MMA issuer   : tcgen05.mma cta_group::1 kind::f16, M=128 x N=NT (16..256), K=16 per
+//                                   instruction, SWIZZLE_128B K-major operands, fp32 accumulators in TMEM
+//                                   (2 x NT columns, double buffered across tiles)
+//   warp 2           TMEM alloc / dealloc
+//   warps 4..7       epilogue     : tcgen05.ld 32x32b.x16 -> bias / act / scale / residual / gate /
+//                                   pixel-shuffle -> 128-bit global stores
+//
+// GEMM view: M = pixels (tile = BH x BW = 128 pixels of one image), N = output channels of one group,
+// K = taps x input channels.  A Linear is the R=S=1 case over a [1,1,rows,K] "image" (tile 1 x 128).
+// Replaces the cuDNN / cuBLAS calls behind nn.Conv2d / nn.Linear on the VMG path.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace vmgb {
+
+struct TcP {
+  int n_img, H, W, Cin_g, Cout_g, groups, R, S, n_src, Cs;
+  int BH, BW, tiles_h, tiles_w, NT, nt_per_g, kb_per_src, stages;
+  long long total_tiles;
+  const float* bias; void* out; const void* res; const void* aux;
+  int out_dt, out_pitch, res_dt, res_pitch, aux_dt, aux_pitch;
+  int act; float alpha, out_scale; int epi; float res_scale; int ps;
+  int b_stage_bytes;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) __trap();     // a lost arrival becomes an error, never a hang
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// SWIZZLE_128B, K-major operand: 8-row groups 1024 B apart (SBO), LBO unused (=1), descriptor version 1
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+constexpr int A_STAGE_BYTES = 128 * 128;   // 128 pixels x 64 bf16
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;            // column offset of the second accumulator
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB, const TcP p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + p.stages * A_STAGE_BYTES;
+  const uint32_t bar_base = b_base + p.stages * p.b_stage_bytes;
+  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base address slot
+  const uint32_t full0 = bar_base, empty0 = bar_base + 8 * p.stages;
+  const uint32_t tfull0 = bar_base + 16 * p.stages, tempty0 = tfull0 + 16;
+  const uint32_t tmem_slot = tempty0 + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int taps = p.R * p.S;
+  const int kblocks = taps * p.n_src * p.kb_per_src;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int ncombo = p.groups * p.nt_per_g;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t tx_bytes = A_STAGE_BYTES + p.NT * 128;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int combo = (int)(tile % ncombo); const long long mt = tile / ncombo;
+      const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+      const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
+      const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
+      for (int tap = 0; tap < taps; ++tap) {
+        const int dh = tap / p.S - p.R / 2, dw = tap % p.S - p.S / 2;
+        const int brow = (g * taps + tap) * p.Cout_g + nt * p.NT;
+        for (int src = 0; src < p.n_src; ++src) {
+          const CUtensorMap* mA = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
+          for (int kb = 0; kb < p.kb_per_src; ++kb) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            mbar_expect_tx(full0 + 8 * stage, tx_bytes);
+            const int ca = (p.n_src > 1 ? 0 : g * p.Cin_g) + kb * 64;
+            tma_load_4d(a_base + stage * A_STAGE_BYTES, mA, full0 + 8 * stage, ca, w0 + dw, h0 + dh, img);
+            tma_load_2d(b_base + stage * p.b_stage_bytes, &mapB, full0 + 8 * stage, src * p.Cs + kb * 64, brow);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int stage = 0; uint32_t phase = 0;
+    uint32_t acc_phase[2] = {0, 0};
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(tempty0 + 8 * as, acc_phase[as] ^ 1);
+      acc_phase[as] ^= 1;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+      uint32_t accumulate = 0;
+      for (int kbi = 0; kbi < kblocks; ++kbi) {
+        const int kb = kbi % p.kb_per_src;
+        const int nks = min(4, (p.Cs - kb * 64 + 15) >> 4);
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        const uint64_t ad = smem_desc_sw128(a_base + stage * A_STAGE_BYTES);
+        const uint64_t bd = smem_desc_sw128(b_base + stage * p.b_stage_bytes);
+        for (int ks = 0; ks < nks; ++ks) {
+          umma_f16(d_tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate);   // +32 B per K step
+          accumulate = 1;
+        }
+        umma_commit(empty0 + 8 * stage);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull0 + 8 * as);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    uint32_t acc_phase[2] = {0, 0};
+    int it = 0;
+    const int nchunks = p.NT >> 4;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const int combo = (int)(tile % ncombo); const long long mt = tile / ncombo;
+      const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+      const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
+      const int hh = (rem / p.tiles_w) * p.BH + row / p.BW, ww = (rem % p.tiles_w) * p.BW + row % p.BW;
+      const bool pvalid = hh < p.H && ww < p.W;
+      const long long pix = ((long long)img * p.H + hh) * p.W + ww;
+      mbar_wait(tfull0 + 8 * as, acc_phase[as]);
+      acc_phase[as] ^= 1;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_STRIDE;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        uint32_t raw[16];
+        __syncwarp();                                  // tcgen05.ld is .sync.aligned: reconverge after masked stores
+        tmem_ld16(taddr + ch * 16, raw);
+        const int nb = nt * p.NT + ch * 16;            // first column of the chunk inside the group
+        if (!pvalid || nb >= p.Cout_g) continue;
+        const int nvalid = min(16, p.Cout_g - nb);
+        const int co0 = g * p.Cout_g + nb;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float t = __uint_as_float(raw[j]);
+          if (p.bias && j < nvalid) t += __ldg(p.bias + co0 + j);
+          v[j] = apply_act(t, p.act, p.alpha) * p.out_scale;
+        }
+        if (p.ps == 2) {
+          // co = 4*c + 2*dy + dx  ->  out[(img, 2h+dy, 2w+dx), c]; 16 columns = 4 channels x 4 sub-pixels
+          const int c0 = co0 >> 2;
+#pragma unroll
+          for (int sp = 0; sp < 4; ++sp) {
+            const long long op = ((long long)img * (2 * p.H) + (2 * hh + (sp >> 1))) * (2 * p.W) + (2 * ww + (sp & 1));
+            if (nvalid == 16) st4(p.out, p.out_dt, op * p.out_pitch + c0, make_float4(v[sp], v[4 + sp], v[8 + sp], v[12 + sp]));
+            else
+              for (int q = 0; q < 4; ++q) if (4 * q + sp < nvalid) stf(p.out, p.out_dt, op * p.out_pitch + c0 + q, v[4 * q + sp]);
+          }
+          continue;
+        }
+        const long long ob = pix * p.out_pitch + co0;
+        const bool vec = nvalid == 16 && ((p.out_pitch | co0) & 3) == 0;
+        if (p.epi != VMGB_EPI_STORE) {
+          const long long rb = pix * p.res_pitch + co0;
+          const bool rvec = nvalid == 16 && ((p.res_pitch | co0) & 3) == 0;
+          float r[16], a[16];
+          if (rvec) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float4 t = ld4(p.res, p.res_dt, rb + 4 * q); r[4 * q] = t.x; r[4 * q + 1] = t.y; r[4 * q + 2] = t.z; r[4 * q + 3] = t.w; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = j < nvalid ? ldf(p.res, p.res_dt, rb + j) : 0.f;
+          }
+          if (p.epi == VMGB_EPI_GATE) {
+            const long long ab = pix * p.aux_pitch + co0;
+            const bool avec = nvalid == 16 && ((p.aux_pitch | co0) & 3) == 0;
+            if (avec) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { const float4 t = ld4(p.aux, p.aux_dt, ab + 4 * q); a[4 * q] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) a[j] = j < nvalid ? ldf(p.aux, p.aux_dt, ab + j) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = r[j] + p.res_scale * ((a[j] + v[j]) * tanhf(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = r[j] + p.res_scale * v[j];
+          }
+        }
+        if (vec) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) st4(p.out, p.out_dt, ob + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (j < nvalid) stf(p.out, p.out_dt, ob + j, v[j]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty0 + 8 * as);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_num_sms = 0;
+static int g_smem_optin = 0;
+static std::once_flag g_once;
+
+static void tc_init() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+    g_encode = (EncodeTiledFn)fn;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (g_smem_optin > 0) cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+}
+
+static bool encode_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                        const cuuint32_t* box) {
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace vmgb
+
+using namespace vmgb;
+
+extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2, int n_src, int x_pitch, const void* w, int Kp,
+                                   const void* bias, void* out, int out_dt, int out_pitch, const void* res, int res_dt,
+                                   int res_pitch, const void* aux, int aux_dt, int aux_pitch, int n_img, int H, int W, int Cin,
+                                   int Cout, int R, int S, int groups, int act, float act_alpha, float out_scale, int epi,
+                                   float res_scale, int pixel_shuffle, int variant, void* stream) {
+  (void)variant;
+  if (!x || !w || !out || !dt_ok(out_dt)) return VMGB_EINVAL;
+  if (n_img <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || groups <= 0 || Cin % groups || Cout % groups) return VMGB_EINVAL;
+  if (!(R & 1) || !(S & 1) || (x_pitch & 7) || (Kp & 15) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15))
+    return VMGB_EINVAL;
+  if (n_src < 1 || n_src > 3 || (n_src > 1 && (!x1 || groups != 1 || Cin % n_src || (Cin / n_src) % 16))) return VMGB_EINVAL;
+  if (n_src > 2 && !x2) return VMGB_EINVAL;
+  if (epi != VMGB_EPI_STORE && (!res || !dt_ok(res_dt))) return VMGB_EINVAL;
+  if (epi == VMGB_EPI_GATE && (!aux || !dt_ok(aux_dt))) return VMGB_EINVAL;
+  if (pixel_shuffle != 0 && (pixel_shuffle != 2 || (Cout & 15) || groups != 1 || epi != VMGB_EPI_STORE || (out_pitch & 3)))
+    return VMGB_EUNSUPPORTED;
+  const int Cin_g = Cin / groups, Cout_g = Cout / groups;
+  if (Kp < Cin_g) return VMGB_EINVAL;
+  std::call_once(g_once, tc_init);
+  if (!g_encode || g_num_sms <= 0) return VMGB_EUNSUPPORTED;
+
+  TcP p;
+  p.n_img = n_img; p.H = H; p.W = W; p.Cin_g = Cin_g; p.Cout_g = Cout_g; p.groups = groups; p.R = R; p.S = S; p.n_src = n_src;
+  p.Cs = n_src > 1 ? Cin / n_src : Cin_g;
+  if (H == 1) { p.BW = 128; p.BH = 1; }
+  else { p.BW = W >= 16 ? 16 : (W >= 8 ? 8 : 4); p.BH = 128 / p.BW; }
+  p.tiles_h = (H + p.BH - 1) / p.BH; p.tiles_w = (W + p.BW - 1) / p.BW;
+  p.nt_per_g = (Cout_g + 255) / 256;
+  p.NT = (((Cout_g + p.nt_per_g - 1) / p.nt_per_g) + 15) / 16 * 16;
+  p.kb_per_src = (p.Cs + 63) / 64;
+  p.b_stage_bytes = (p.NT * 128 + 1023) / 1024 * 1024;
+  const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
+  const int budget = g_smem_optin - 1024 - 256;
+  p.stages = budget / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) return VMGB_EUNSUPPORTED;
+  p.total_tiles = (long long)n_img * p.tiles_h * p.tiles_w * groups * p.nt_per_g;
+  p.bias = (const float*)bias; p.out = out; p.res = res; p.aux = aux;
+  p.out_dt = out_dt; p.out_pitch = out_pitch; p.res_dt = res_dt; p.res_pitch = res_pitch; p.aux_dt = aux_dt; p.aux_pitch = aux_pitch;
+  p.act = act; p.alpha = act_alpha; p.out_scale = out_scale; p.epi = epi; p.res_scale = res_scale; p.ps = pixel_shuffle;
+
+  // activation maps: dims (C, W, H, N) ; channel extent = the source's own channel count so that the
+  // K tail and the virtual-concat boundary are zero-filled by TMA
+  CUtensorMap mA[3], mB;
+  const void* srcs[3] = {x, x1, x2};
+  const int c_extent = n_src > 1 ? p.Cs : Cin;
+  for (int s = 0; s < 3; ++s) {
+    const void* ptr = s < n_src ? srcs[s] : x;
+    if (reinterpret_cast<uintptr_t>(ptr) & 15) return VMGB_EINVAL;
+    cuuint64_t dims[4] = {(cuuint64_t)c_extent, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+    cuuint64_t str[3] = {(cuuint64_t)x_pitch * 2, (cuuint64_t)W * x_pitch * 2, (cuuint64_t)H * W * x_pitch * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
+    if (!encode_bf16(&mA[s], ptr, 4, dims, str, box)) return VMGB_EINVAL;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)groups * R * S * Cout_g};
+    cuuint64_t str[1] = {(cuuint64_t)Kp * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)p.NT};
+    if (!encode_bf16(&mB, w, 2, dims, str, box)) return VMGB_EINVAL;
+  }
+  const int smem = p.stages * stage_bytes + 1024 + 256;
+  const long long grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  conv_tc_kernel<<<(unsigned)grid, 256, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
+  return check_launch();
+}
