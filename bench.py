@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the VMG model-forward hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+A "step" is one VMG forward over one synthetic REDS4-shaped clip per GPU (BASELINE.json configs[1]:
+VMG-REDS full model, 100 frames 180x320 -> 720x1280, bf16 tcgen05 path).  Multi-GPU = one process per
+GPU (torchrun), one clip per rank, no data-path collective (clips are independent): weak scaling.
+
+Reported on ONE JSON line: `value` = 720p output frames/s with inputs resident in HBM (CUDA events,
+max over ranks); `e2e` = same through the public nn.Module call with pinned-host input and output copies
+inside the timed region; `roofline` = tensor-pipe fraction of the dominant kernel (conv_tc_kernel) from
+per-launch CUDA events in one extra instrumented forward; `cpu_baseline` = the CPU oracle
+(oracle/vmg_oracle.py, a port of the reference forward) on a bounded sample, rank 0, N=1 only.
+`--impl reference` times that CPU oracle as the reference arm (the reference is pure PyTorch; its
+own CPU path is what tools/cpu_test.sh runs).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = '720p output frames/sec (4x VSR, REDS shape)'
+UNIT = 'frames/s'
+REF_PIX = 180 * 320           # LQ pixels behind one 720p output frame
+
+WORKLOADS = {
+    # name: (config yml, B, T, H, W)
+    'reds4_full_100x180x320': ('VMG-REDS.yml', 1, 100, 180, 320),
+    'reds4_few_100x180x320': ('VMG-REDS-few_levels.yml', 1, 100, 180, 320),
+    'tile_full_50x128x128': ('VMG-REDS.yml', 1, 50, 128, 128),
+    'small_full_7x64x64': ('VMG-REDS.yml', 1, 7, 64, 64),
+}
+DEFAULT_WORKLOAD = 'reds4_full_100x180x320'
+CPU_SAMPLE = (1, 7, 64, 64)   # bounded CPU sample of the same model (FLOPs are linear in T*H*W)
+
+
+def synthetic_clip(B, T, H, W, seed):
+    """Deterministic smooth moving field in [0,1] (sum of seeded low-frequency sinusoids translating
+    <= 2 px/frame) -- realistic scatter for the warp / trajectory kernels, unlike white noise."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing='ij')
+    clip = torch.zeros(B, T, 3, H, W)
+    for b in range(B):
+        vel = (torch.rand(2, generator=g) * 4 - 2)
+        for c in range(3):
+            acc = torch.zeros(T, H, W)
+            for _ in range(8):
+                fx, fy = (torch.rand(2, generator=g) * 0.25 + 0.01).tolist()
+                ph = (torch.rand(1, generator=g) * 6.28).item()
+                amp = (torch.rand(1, generator=g) * 0.5 + 0.1).item()
+                t = torch.arange(T, dtype=torch.float32)[:, None, None]
+                acc += amp * torch.sin(fx * (xx[None] + vel[0] * t) + fy * (yy[None] + vel[1] * t) + ph)
+            clip[b, :, c] = acc
+    clip = (clip - clip.amin()) / (clip.amax() - clip.amin())
+    return clip.contiguous()
+
+
+def model_kwargs(yml):
+    from vmg_b200 import config as cfg
+    c = cfg.parse_config(os.path.join(ROOT, 'configs', yml), is_train=False)
+    return cfg.model_kwargs(c)
+
+
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.FIELDS}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([s.strip() for s in line.split(',')])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith('active') for r in self.rows)]
+        busy = [s for s in sm if s > 0]
+        return {'sm_mhz': busy[len(busy) // 2] if busy else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(self.rows)}
+
+
+def run_cpu_oracle(kw, steps, warmup, threads):
+    """Times the CPU oracle (port of the reference forward) on the bounded sample.  Returns (fps, s/step)."""
+    from oracle import vmg_oracle
+    from vmg_b200.model import VMG
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    sd = {k: v.clone() for k, v in VMG(**kw).state_dict().items()}
+    B, T, H, W = CPU_SAMPLE
+    x = synthetic_clip(B, T, H, W, seed=1)
+    hp = vmg_oracle.Hyper(**kw)
+    hp.num_out_frames = T
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            vmg_oracle.forward(sd, hp, x)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return B * T * H * W / REF_PIX / sec, sec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='vmg_b200', choices=['vmg_b200', 'reference'])
+    ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    yml, B, T, H, W = WORKLOADS[args.workload]
+    kw = model_kwargs(yml)
+    config = {'workload': args.workload, 'model_config': yml, 'clip': [B, T, 3, H, W], 'clips_per_gpu': 1,
+              'parallelism': f'clip-sharded x{world}' if world > 1 else 'single GPU',
+              'l2_policy': 'activations per step are GBs (>> 126 MB L2); no explicit flush needed'}
+
+    # ------------------------------------------------------------------ reference arm (CPU oracle)
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        fps, sec = run_cpu_oracle(kw, max(1, args.steps), max(1, min(args.warmup, 1)), threads)
+        sample = f'oracle forward on a {CPU_SAMPLE[1]}x{CPU_SAMPLE[2]}x{CPU_SAMPLE[3]} crop of the workload, same model, fp32, warm'
+        print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+                          'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+                          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                          'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+                          'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    # ------------------------------------------------------------------ product arm
+    import torch.distributed as dist
+    from vmg_b200 import ops
+    from vmg_b200.model import VMG
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    torch.manual_seed(0)
+    model = VMG(**kw, precision=args.precision).eval().cuda()
+    model.num_out_frames = T
+    x_host = synthetic_clip(B, T, H, W, seed=1 + rank).pin_memory()
+    x_dev = x_host.cuda(non_blocking=True)
+    out_host = torch.empty((B, T, 3, 4 * H, 4 * W), dtype=torch.float32).pin_memory()
+    frames_per_step = B * T * H * W / REF_PIX
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        model(x_dev)
+    # ---- device-resident timing
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    n0 = ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        y = model(x_dev)
+    ev1.record()
+    barrier()
+    launches = ops.launch_count() - n0
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = world * frames_per_step / (ms_step * 1e-3)
+    # ---- end to end: pinned host input -> H2D -> forward -> D2H of the output frames
+    model(x_host.cuda(non_blocking=True))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        xd = x_host.cuda(non_blocking=True)
+        y = model(xd)
+        out_host.copy_(y, non_blocking=True)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e = {'value': world * frames_per_step / (e2e_ms * 1e-3), 'unit': UNIT,
+           'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': out_host.numel() * 4, 'ms_per_step': e2e_ms}
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream (instrumented forward)
+    roofline = None
+    if rank == 0:
+        recs = []
+        real = ops.lib().vmgb_conv2d_nhwc_tc
+
+        def timed(*a):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = real(*a)
+            e.record()
+            # C prototype positions 17..24 = n_img,H,W,Cin,Cout,R,S,groups
+            n_img, h, w, cin, cout, r, s_, g = a[17:25]
+            recs.append((s, e, 2.0 * n_img * h * w * cout * r * s_ * (cin // g)))
+            return rc
+        ops.lib().vmgb_conv2d_nhwc_tc = timed
+        try:
+            model(x_dev)
+            torch.cuda.synchronize()
+        finally:
+            ops.lib().vmgb_conv2d_nhwc_tc = real
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = peaks.get('bf16_tflops_sustained', 1400.0)
+        src = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if 'bf16_tflops_sustained' in peaks else 'fallback 1.4 PFLOP/s sustained (of fallback)'
+        if recs:
+            tot_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+            tot_fl = sum(f for _, _, f in recs)
+            ach = tot_fl / (tot_ms * 1e-3) / 1e12
+            roofline = {'kernel': 'conv_tc_kernel', 'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                        'traffic': None, 'launches': len(recs), 'kernel_ms_per_step': tot_ms, 'share_of_step': tot_ms / ms_step,
+                        'algorithmic_tflop_per_step': tot_fl / 1e12, 'peak_source': src}
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        fps, sec = run_cpu_oracle(kw, 2, 1, threads)
+        cpu_baseline = {'value': fps, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'seconds_per_sample': sec,
+                        'sample': f'oracle (CPU port of the reference forward) on a {CPU_SAMPLE[1]}x{CPU_SAMPLE[2]}x{CPU_SAMPLE[3]} crop, same model, fp32, 2 warm calls'}
+    if rank == 0:
+        print(json.dumps({'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                          'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                          'dtype': args.precision, 'data': 'synthetic', 'config': config, 'clocks': clocks, 'e2e': e2e,
+                          'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

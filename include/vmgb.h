@@ -87,7 +87,9 @@ int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2, int n_src
                         int act, float act_alpha, float out_scale, int epi, float res_scale,
                         int pixel_shuffle, int variant, void* stream);
 
-/* OIHW fp32 conv weight [Cout][Cin/groups][R][S] (or Linear [Cout][Cin], R=S=1) -> packed layouts. */
+/* OIHW fp32 conv weight [Cout][Cin/groups][R][S] (or Linear [Cout][Cin], R=S=1) -> packed layouts.
+ * tc layout: input channel ci of group g is stored at k = ((g*Cin/groups) % 8) + ci, so
+ * Kp >= Cin/groups + max_g((g*Cin/groups) % 8), Kp % 16 == 0. */
 int vmgb_pack_weight(const void* w_oihw, void* w_packed, int Cout, int Cin_g, int R, int S, int groups, void* stream);
 int vmgb_pack_weight_tc(const void* w_oihw, void* w_packed_bf16, int Cout, int Cin_g, int Kp, int R, int S, int groups, void* stream);
 

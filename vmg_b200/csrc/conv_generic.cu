@@ -176,7 +176,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
   }
 }
 
-// OIHW fp32 -> [G][R*S][Cout_g][Kp] bf16 (zero padded K)
+// OIHW fp32 -> [G][R*S][Cout_g][Kp] bf16, zero padded K; input channel ci of group g sits at
+// k = ((g*Cin_g) & 7) + ci so that the kernel can start its TMA box at a 16-byte aligned channel
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout, int Cin_g, int Kp, int taps, int groups) {
   const int Cout_g = Cout / groups;
   const long long total = (long long)groups * taps * Cout_g * Kp;
@@ -184,7 +185,8 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16
     int k = (int)(i % Kp); long long r = i / Kp;
     int n = (int)(r % Cout_g); r /= Cout_g;
     int tap = (int)(r % taps); int g = (int)(r / taps);
-    float v = k < Cin_g ? w[((long long)(g * Cout_g + n) * Cin_g + k) * taps + tap] : 0.f;
+    const int ci = k - ((g * Cin_g) & 7);
+    float v = (ci >= 0 && ci < Cin_g) ? w[((long long)(g * Cout_g + n) * Cin_g + ci) * taps + tap] : 0.f;
     o[i] = __float2bfloat16_rn(v);
   }
 }

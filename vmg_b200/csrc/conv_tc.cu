@@ -152,7 +152,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           for (int kb = 0; kb < p.kb_per_src; ++kb) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             mbar_expect_tx(full0 + 8 * stage, tx_bytes);
-            const int ca = (p.n_src > 1 ? 0 : g * p.Cin_g) + kb * 64;
+            // grouped conv: start the box at a 16-byte aligned channel; the packed weights of the group are
+            // shifted by the same `koff` rows of zeros (vmgb_pack_weight_tc)
+            const int ca = (p.n_src > 1 ? 0 : ((g * p.Cin_g) & ~7)) + kb * 64;
             tma_load_4d(a_base + stage * A_STAGE_BYTES, mA, full0 + 8 * stage, ca, w0 + dw, h0 + dh, img);
             tma_load_2d(b_base + stage * p.b_stage_bytes, &mapB, full0 + 8 * stage, src * p.Cs + kb * 64, brow);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -173,9 +175,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
       uint32_t accumulate = 0;
+      const int g_mma = (int)(tile % ncombo) / p.nt_per_g;
+      const int kext = p.Cs + (p.n_src > 1 ? 0 : ((g_mma * p.Cin_g) & 7));     // K extent incl. the alignment shift
       for (int kbi = 0; kbi < kblocks; ++kbi) {
         const int kb = kbi % p.kb_per_src;
-        const int nks = min(4, (p.Cs - kb * 64 + 15) >> 4);
+        const int nks = min(4, (kext - kb * 64 + 15) >> 4);
         mbar_wait(full0 + 8 * stage, phase);
         tc_fence_after();
         const uint64_t ad = smem_desc_sw128(a_base + stage * A_STAGE_BYTES);
@@ -351,7 +355,10 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   p.tiles_h = (H + p.BH - 1) / p.BH; p.tiles_w = (W + p.BW - 1) / p.BW;
   p.nt_per_g = (Cout_g + 255) / 256;
   p.NT = (((Cout_g + p.nt_per_g - 1) / p.nt_per_g) + 15) / 16 * 16;
-  p.kb_per_src = (p.Cs + 63) / 64;
+  int max_koff = 0;
+  for (int g = 0; g < groups; ++g) max_koff = max(max_koff, (g * Cin_g) & 7);
+  if (Kp < Cin_g + max_koff) return VMGB_EINVAL;
+  p.kb_per_src = (p.Cs + max_koff + 63) / 64;
   p.b_stage_bytes = (p.NT * 128 + 1023) / 1024 * 1024;
   const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
   const int budget = g_smem_optin - 1024 - 256;

@@ -142,7 +142,8 @@ def pack_conv(weight, bias, groups=1, tc=False):
     _ck(lib().vmgb_pack_weight(w.data_ptr(), pc.w32.data_ptr(), Cout, Cin_g, R, S, groups, _stream()), 'vmgb_pack_weight')
     pc.wtc, pc.Kp = None, 0
     if tc:
-        pc.Kp = (Cin_g + 15) // 16 * 16
+        koff = max((g * Cin_g) % 8 for g in range(groups))     # 16-byte alignment shift of grouped convs
+        pc.Kp = (Cin_g + koff + 15) // 16 * 16
         pc.wtc = torch.empty(groups * R * S * (Cout // groups) * pc.Kp, device=w.device, dtype=torch.bfloat16)
         _ck(lib().vmgb_pack_weight_tc(w.data_ptr(), pc.wtc.data_ptr(), Cout, Cin_g, pc.Kp, R, S, groups, _stream()),
             'vmgb_pack_weight_tc')
