@@ -134,6 +134,7 @@ def main():
     ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-mode', action='store_true', help='warm-up + timed steps only (for ncu runs)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -204,6 +205,10 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * frames_per_step / (ms_step * 1e-3)
+    if args.profile_mode:
+        if rank == 0:
+            print(json.dumps({'profile_mode': True, 'ms_per_step': ms_step, 'value': value, 'gpu_launches': launches}))
+        return
     # ---- end to end: pinned host input -> H2D -> forward -> D2H of the output frames
     model(x_host.cuda(non_blocking=True))
     barrier()

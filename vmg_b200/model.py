@@ -10,6 +10,7 @@ Internal layout: channels-last, frames time-major: activations are [T*B, H, W, C
 """
 from fractions import Fraction
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -277,6 +278,8 @@ class VMG(nn.Module):
         self.mlp_wd_param = [p for name, p in self.named_parameters() if '.mlp_blocks.' in name]
         self.apply(self._init_weights)
         self._packed = {}
+        self._graphs, self._graph_stamp = {}, None
+        self.use_cuda_graph = os.environ.get('VMGB_NO_GRAPH', '0') != '1'
         self.recon_chunk = 8     # frames per reconstruction-head chunk (bounds the 4x-resolution temporaries)
 
     @staticmethod
@@ -469,8 +472,16 @@ class VMG(nn.Module):
         u = o.linear(u, self._pc(sc[0]))
         return o.groupnorm1_relu(u, sc[1].weight, sc[1].bias)
 
+    def _weights_stamp(self):
+        """Changes whenever a parameter/buffer is re-assigned or written through torch (load_state_dict,
+        .to(), optimiser steps); the in-kernel decay writes do not bump it by design."""
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
     @torch.no_grad()
     def forward(self, x, flow_pretrained=None, config_amp=None):
+        """models/vmg.py:585-637.  The launch sequence of one (shape, mirror) signature is captured into a
+        CUDA graph on its second call and replayed afterwards (the reference issues ~4 300 ATen ops per
+        frame; the sequential trajectory sweeps are launch-latency bound otherwise)."""
         o = _ops
         o.require_device()
         if self.training:
@@ -481,10 +492,37 @@ class VMG(nn.Module):
             raise RuntimeError(f'shape mismatch: T={T} but num_out_frames={self.num_out_frames} (models/vmg.py:635)')
         x = x.contiguous().float()
         self.frames_mirror = o.mirror_check(x)                            # vmg.py:426-432
+        if not (self.use_cuda_graph and x.is_cuda and hasattr(torch.cuda, 'CUDAGraph')):
+            return self._forward_impl(x, self.frames_mirror)
+        stamp = self._weights_stamp()
+        if stamp != self._graph_stamp:
+            self._graphs.clear()
+            self._graph_stamp = stamp
+        key = (tuple(x.shape), self.frames_mirror, self.precision, x.device.index)
+        ent = self._graphs.get(key)
+        if ent is None:                       # first call: eager (also packs the weights)
+            self._graphs[key] = 'warm'
+            return self._forward_impl(x, self.frames_mirror)
+        if ent == 'warm':                     # second call: capture
+            xs = x.clone()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                ys = self._forward_impl(xs, self.frames_mirror)
+            ent = (g, xs, ys)
+            self._graphs[key] = ent
+        g, xs, ys = ent
+        xs.copy_(x)
+        g.replay()
+        return ys.clone()
+
+    def _forward_impl(self, x, mirror):
+        o = _ops
+        B, T, Cin, H, W = x.shape
         Hp = int(math.ceil(H / self.scale)) * self.scale
         Wp = int(math.ceil(W / self.scale)) * self.scale
         xp = o.pad_input(x, Hp, Wp)                                       # [T*B,Hp,Wp,3] fp32
-        flows = self._compute_flow(xp, B, T, self.frames_mirror)
+        flows = self._compute_flow(xp, B, T, mirror)
         adt = self._adt
         E, D = self.encoder_layers, self.decoder_layers
         x0 = o.conv2d(xp, self._pc(self.input_proj.proj[0], tc=False), act=o.ACT_LRELU, alpha=0.01, out_dtype=adt,
