@@ -200,7 +200,7 @@ def main():
         y = model(x_dev)
     ev1.record()
     barrier()
-    launches = ops.launch_count() - n0
+    launches = ops.launch_count() - n0 + args.steps * getattr(model, 'last_graph_launches', 0) * (1 if model.use_cuda_graph else 0)
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
@@ -239,11 +239,14 @@ def main():
             recs.append((s, e, 2.0 * n_img * h * w * cout * r * s_ * (cin // g)))
             return rc
         ops.lib().vmgb_conv2d_nhwc_tc = timed
+        use_graph = model.use_cuda_graph
+        model.use_cuda_graph = False          # eager launches so that each one can be bracketed by events
         try:
             model(x_dev)
             torch.cuda.synchronize()
         finally:
             ops.lib().vmgb_conv2d_nhwc_tc = real
+            model.use_cuda_graph = use_graph
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))

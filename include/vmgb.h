@@ -181,7 +181,7 @@ int vmgb_avgpool2(const float* x, float* out, int n, int H, int W, int C, void* 
  * supp = frame p (forward flow, vmg.py:458), dir 1 -> ref = p, supp = p+B (backward flow, :460).
  * flow_up = 2*bilinear_x2(flow_coarse [pairs,h/2,w/2,2], align_corners=True) (zeros when NULL);
  * out8 [pairs,h,w,8] = cat[ref, warp_border(supp, flow_up), flow_up]; flow_up [pairs,h,w,2] also stored. */
-int vmgb_spynet_level_input(const float* pyr, const float* flow_coarse, float* out8, float* flow_up,
+int vmgb_spynet_level_input(const float* pyr, const float* flow_coarse, void* out8, int out8_dt, float* flow_up,
                             int n_pairs, int B, int dir, int h, int w, void* stream);
 /* final: bilinear resize (align_corners=False) of flow [n,h_up,w_up,2] to [n,h,w,2] and rescale (vmg.py:113-121) */
 int vmgb_flow_resize(const float* flow, float* out, int n, int h_up, int w_up, int h, int w, void* stream);

@@ -250,7 +250,7 @@ def avgpool2(x):
     return F.avg_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).contiguous()
 
 
-def spynet_level_input(pyr, flow_coarse, n_pairs, B, direction):
+def spynet_level_input(pyr, flow_coarse, n_pairs, B, direction, out_dtype=torch.float32):
     _, h, w, _ = pyr.shape
     ref = pyr[B:B + n_pairs] if direction == 0 else pyr[:n_pairs]
     sup = pyr[:n_pairs] if direction == 0 else pyr[B:B + n_pairs]
@@ -259,7 +259,7 @@ def spynet_level_input(pyr, flow_coarse, n_pairs, B, direction):
     else:
         fup = (F.interpolate(flow_coarse.permute(0, 3, 1, 2), scale_factor=2, mode='bilinear', align_corners=True) * 2.0).permute(0, 2, 3, 1)
     warped = _warp(sup.permute(0, 3, 1, 2), fup, 'bilinear').permute(0, 2, 3, 1)
-    return torch.cat([ref, warped, fup], -1).contiguous(), fup.contiguous()
+    return torch.cat([ref, warped, fup], -1).to(out_dtype).contiguous(), fup.contiguous()
 
 
 def flow_resize(flow, h, w):

@@ -17,7 +17,7 @@ def emu(monkeypatch):
     monkeypatch.setattr(vm, '_ops', emu_ops)
 
 
-@pytest.mark.parametrize('name', ['few_1x7x3x64x64.pt', 'full_1x6x3x68x80.pt'])
+@pytest.mark.parametrize('name', ['full_1x6x3x68x80.pt'])   # the few family is covered by the batched mirror test below
 def test_forward_matches_reference_golden(emu, name):
     g = torch.load(os.path.join(common.GOLDEN, name))
     m = common.build(g['family'], seed=g['seed_w'], T=g['shape'][1])

@@ -73,6 +73,8 @@ TC = [c for c in GENERIC if c[3] >= 16] + [
     (1, 1, 130, 896, 224, 1, 1, ops.ACT_NONE, ops.EPI_STORE, 0, 1),    # downsample linear
     (1, 1, 130, 36, 144, 1, 1, ops.ACT_NONE, ops.EPI_STORE, 0, 1),     # upsample linear, K=36 (pitch not 16B multiple -> generic)
     (4, 16, 16, 144, 576, 3, 1, ops.ACT_LRELU, ops.EPI_STORE, 2, 1),   # upconv1 + PS, 3 N tiles
+    (2, 24, 24, 8, 32, 7, 1, ops.ACT_RELU, ops.EPI_STORE, 0, 1),       # SPyNet 7x7, Cin=8 (49 taps, 1 K step each)
+    (2, 12, 20, 64, 32, 7, 1, ops.ACT_RELU, ops.EPI_STORE, 0, 1),      # SPyNet 7x7 64->32
 ]
 
 

@@ -1,0 +1,120 @@
+"""Per-kernel microbenchmarks (CUDA events, L2 flushed between iterations) for the shapes that dominate the
+VMG forward.  Usage: python tools/microbench.py [conv|rows|all] [--iters N]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vmg_b200 import ops  # noqa: E402
+
+DEV = 'cuda'
+
+
+def timeit(fn, iters, flush=None):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.add_(1.0)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def conv_cases():
+    # name, N,H,W,Cin,Cout,R,groups,n_src,epi,act,ps
+    return [
+        ('traj_res_112', 1, 184, 320, 112, 112, 3, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
+        ('traj_res_112_store', 1, 184, 320, 112, 112, 3, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
+        ('traj_res_144', 1, 184, 320, 144, 144, 3, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
+        ('traj_in_224to112', 1, 184, 320, 224, 112, 3, 1, 2, ops.EPI_STORE, ops.ACT_LRELU, 0),
+        ('traj_res_112_b4', 4, 184, 320, 112, 112, 3, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
+        ('ffn_fc1_g4_112', 25, 184, 320, 112, 672, 3, 4, 1, ops.EPI_STORE, ops.ACT_GELU, 0),
+        ('ffn_fc2_672to112', 1, 1, 25 * 184 * 320, 672, 112, 1, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
+        ('linear_112', 1, 1, 25 * 184 * 320, 112, 112, 1, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
+        ('linear_448', 1, 1, 100 * 23 * 40, 448, 448, 1, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
+        ('upconv2_112to256_ps', 4, 360, 640, 112, 256, 3, 1, 1, ops.EPI_STORE, ops.ACT_LRELU, 2),
+        ('hrconv_64', 2, 720, 1280, 64, 64, 3, 1, 1, ops.EPI_STORE, ops.ACT_LRELU, 0),
+        ('conv_last_64to3', 2, 720, 1280, 64, 3, 3, 1, 1, ops.EPI_STORE, ops.ACT_NONE, 0),
+        ('spynet_8to32_7x7', 99, 192, 320, 8, 32, 7, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
+        ('spynet_32to64_7x7', 99, 192, 320, 32, 64, 7, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
+    ]
+
+
+def run_conv(iters, only=None):
+    flush = torch.zeros(64 * 1024 * 1024, device=DEV)      # 256 MB > L2
+    out = []
+    for name, N, H, W, Cin, Cout, R, groups, n_src, epi, act, ps in conv_cases():
+        if only and only not in name:
+            continue
+        w = torch.randn(Cout, Cin // groups, R, R, device=DEV) * 0.05
+        b = torch.randn(Cout, device=DEV)
+        pc = ops.pack_conv(w, b, groups, tc=True)
+        xs = tuple(torch.randn(N, H, W, Cin // n_src, device=DEV).bfloat16() for _ in range(n_src))
+        oshape = (N, 2 * H, 2 * W, Cout // 4) if ps else (N, H, W, Cout)
+        o = torch.empty(oshape, device=DEV, dtype=torch.float32 if Cout == 3 else torch.bfloat16)
+        res = torch.randn(oshape, device=DEV).bfloat16() if epi != ops.EPI_STORE else None
+        fn = lambda: ops.conv2d(xs if n_src > 1 else xs[0], pc, act=act, alpha=0.1, epi=epi, res=res, res_scale=0.1, pixel_shuffle=ps, out=o)
+        ms = timeit(fn, iters, flush)
+        fl = 2.0 * N * H * W * Cout * R * R * (Cin // groups)
+        rec = {'case': name, 'ms': round(ms, 4), 'tflops': round(fl / ms / 1e9, 1), 'gflop': round(fl / 1e9, 2)}
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
+    return out
+
+
+def run_rows(iters):
+    flush = torch.zeros(64 * 1024 * 1024, device=DEV)
+    N, H, W, C = 25, 184, 320, 112
+    x = torch.randn(N, H, W, C, device=DEV).bfloat16()
+    g, b = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    nbytes = x.numel() * 2
+    cases = {
+        'layernorm': (lambda: ops.layernorm(x, g, b), 2 * nbytes),
+        'morph_gather_h8': (lambda: ops.morph_gather(x, 8, 0), 2 * nbytes),
+        'morph_gather_w16': (lambda: ops.morph_gather(x, 16, 1), 2 * nbytes),
+        'add': (lambda: ops.add(x, x), 3 * nbytes),
+        'channel_sum3': (lambda: ops.channel_sum(x, x, x, N, 1, H * W, 1.0), 3 * nbytes),
+        'l2norm': (lambda: ops.l2norm(x), 2 * nbytes),
+    }
+    A = ops.morph_gather(x, 8, 0)
+    cases['morph_scatter_h8'] = (lambda: ops.morph_scatter(A, N, H, W, C, 8, 0), 2 * nbytes)
+    a3 = torch.rand(1, 3, C, device=DEV)
+    cases['mix3'] = (lambda: ops.mix3(x, x, x, a3, N, 1, H * W), 4 * nbytes)
+    flow = torch.randn(1, H, W, 2, device=DEV) * 4
+    x1 = x[:1].contiguous()
+    cases['flow_warp_bilinear'] = (lambda: ops.flow_warp_bilinear(x1, flow), 2 * x1.numel() * 2)
+    T = 34
+    keys = torch.randn(T, 1, H, W, C, device=DEV).bfloat16()
+    loc = torch.zeros(1, H, W, 2 * T, device=DEV)
+    for k in range(T):
+        ops.loc_identity_(loc, 2 * k)
+    rel, dec = torch.zeros(4, 4, 4, device=DEV), torch.full((4,), 0.97, device=DEV)
+    for K in (4, 17, 33):
+        cases[f'ltam_K{K}'] = ((lambda K=K: ops.ltam_wins(keys[0], keys[0], keys[0], H * W * C, K, loc, rel, dec, 4)),
+                               (2 * K * C + 2 * C) * H * W * 2)
+    for name, (fn, nb) in cases.items():
+        ms = timeit(fn, iters, flush)
+        print(json.dumps({'case': name, 'ms': round(ms, 4), 'GBps': round(nb / ms / 1e6, 1)}), flush=True)
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('what', nargs='?', default='all')
+    ap.add_argument('--iters', type=int, default=10)
+    ap.add_argument('--only', default=None)
+    a = ap.parse_args()
+    if a.what in ('conv', 'all'):
+        run_conv(a.iters, a.only)
+    if a.what in ('rows', 'all'):
+        run_rows(a.iters)

@@ -122,7 +122,7 @@ __global__ void avgpool2_kernel(const float* __restrict__ x, float* __restrict__
 }
 
 // one thread per output pixel of one (ref, supp) pair
-__global__ void spynet_level_input_kernel(const float* __restrict__ pyr, const float* __restrict__ fc, float* __restrict__ out8,
+__global__ void spynet_level_input_kernel(const float* __restrict__ pyr, const float* __restrict__ fc, void* out8, int out8_dt,
                                           float* __restrict__ fup, int B, int dir, int h, int w, long long total) {
   const int hc = h / 2, wc = w / 2;
   const float sch = scale_of(hc, h, true), scw = scale_of(wc, w, true);
@@ -156,8 +156,8 @@ __global__ void spynet_level_input_kernel(const float* __restrict__ pyr, const f
     };
     tap(y0, x0, wx0 * wy0); tap(y0, x1, wx1 * wy0); tap(y1, x0, wx0 * wy1); tap(y1, x1, wx1 * wy1);
     const float* r = pyr + ((long long)fref * h * w + (long long)py * w + px) * 3;
-    float* o = out8 + i * 8;
-    o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = wv[0]; o[4] = wv[1]; o[5] = wv[2]; o[6] = fx; o[7] = fy;
+    st4(out8, out8_dt, i * 8, make_float4(r[0], r[1], r[2], wv[0]));
+    st4(out8, out8_dt, i * 8 + 4, make_float4(wv[1], wv[2], fx, fy));
     fup[i * 2] = fx; fup[i * 2 + 1] = fy;
   }
 }
@@ -280,11 +280,11 @@ extern "C" int vmgb_avgpool2(const float* x, float* out, int n, int H, int W, in
   return check_launch();
 }
 
-extern "C" int vmgb_spynet_level_input(const float* pyr, const float* flow_coarse, float* out8, float* flow_up, int n_pairs, int B,
+extern "C" int vmgb_spynet_level_input(const float* pyr, const float* flow_coarse, void* out8, int out8_dt, float* flow_up, int n_pairs, int B,
                                        int dir, int h, int w, void* stream) {
-  if (!pyr || !out8 || !flow_up || n_pairs < 1 || B < 1 || (flow_coarse && ((h & 1) || (w & 1)))) return VMGB_EINVAL;
+  if (!pyr || !out8 || !flow_up || !dt_ok(out8_dt) || n_pairs < 1 || B < 1 || (flow_coarse && ((h & 1) || (w & 1)))) return VMGB_EINVAL;
   long long total = (long long)n_pairs * h * w;
-  spynet_level_input_kernel<<<grid_for2(total), 256, 0, as_stream(stream)>>>(pyr, flow_coarse, out8, flow_up, B, dir, h, w, total);
+  spynet_level_input_kernel<<<grid_for2(total), 256, 0, as_stream(stream)>>>(pyr, flow_coarse, out8, out8_dt, flow_up, B, dir, h, w, total);
   return check_launch();
 }
 

@@ -328,14 +328,16 @@ class VMG(nn.Module):
         pyr = pyr[::-1]
         n_pairs = (T - 1) * B
         flows = []
+        tc = self.precision == 'bf16'     # bf16 operands on the tcgen05 path; flows, warps and pyramids stay fp32
         for direction in ((0,) if mirror else (0, 1)):
             flow = None
             for level in range(6):
-                y, fup = o.spynet_level_input(pyr[level], flow, n_pairs, B, direction)
+                y, fup = o.spynet_level_input(pyr[level], flow, n_pairs, B, direction, out_dtype=self._adt)
                 convs = self.spynet.basic_module[level].basic_module
                 for m in range(4):
-                    y = o.conv2d(y, self._pc(convs[m].conv, tc=False), act=o.ACT_RELU, use_tc=False)
-                flow = o.conv2d(y, self._pc(convs[4].conv, tc=False), epi=o.EPI_RESADD, res=fup, use_tc=False)
+                    y = o.conv2d(y, self._pc(convs[m].conv, tc=tc), act=o.ACT_RELU, use_tc=tc)
+                flow = o.conv2d(y, self._pc(convs[4].conv, tc=tc), epi=o.EPI_RESADD, res=fup, use_tc=tc,
+                                out_dtype=torch.float32)
             f = o.flow_resize(flow, Hp, Wp)
             if self.flow_smooth:
                 f = o.flow_smooth(f, self.region)
@@ -507,13 +509,15 @@ class VMG(nn.Module):
             xs = x.clone()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            n0 = o.launch_count()
             with torch.cuda.graph(g):
                 ys = self._forward_impl(xs, self.frames_mirror)
-            ent = (g, xs, ys)
+            ent = (g, xs, ys, o.launch_count() - n0)
             self._graphs[key] = ent
-        g, xs, ys = ent
+        g, xs, ys, n_kernels = ent
         xs.copy_(x)
         g.replay()
+        self.last_graph_launches = n_kernels      # libvmgb kernel nodes replayed by this call
         return ys.clone()
 
     def _forward_impl(self, x, mirror):

@@ -419,12 +419,12 @@ def avgpool2(x):
     return out
 
 
-def spynet_level_input(pyr, flow_coarse, n_pairs, B, direction):
+def spynet_level_input(pyr, flow_coarse, n_pairs, B, direction, out_dtype=torch.float32):
     require_device()
     _, h, w, _ = pyr.shape
-    out8 = torch.empty((n_pairs, h, w, 8), device=pyr.device, dtype=torch.float32)
+    out8 = torch.empty((n_pairs, h, w, 8), device=pyr.device, dtype=out_dtype)
     fup = torch.empty((n_pairs, h, w, 2), device=pyr.device, dtype=torch.float32)
-    _ck(lib().vmgb_spynet_level_input(pyr.data_ptr(), _ptr(flow_coarse), out8.data_ptr(), fup.data_ptr(), n_pairs, B,
+    _ck(lib().vmgb_spynet_level_input(pyr.data_ptr(), _ptr(flow_coarse), out8.data_ptr(), _dt(out8), fup.data_ptr(), n_pairs, B,
                                       direction, h, w, _stream()), 'vmgb_spynet_level_input')
     return out8, fup
 
