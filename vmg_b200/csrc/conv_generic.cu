@@ -130,6 +130,43 @@ __global__ void __launch_bounds__(256) conv_generic_kernel(ConvP p) {
   }
 
   // ---- epilogue -------------------------------------------------------------------------------
+  // activation applied tile-wide behind ONE warp-uniform switch (bias first)
+  {
+    float bj[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int ng = n0 + tx * 4 + j; bj[j] = (p.bias && ng < p.Cout_g) ? p.bias[g * p.Cout_g + ng] : 0.f; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += bj[j];
+    switch (p.act) {
+      case VMGB_ACT_RELU:
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaxf(acc[i][j], 0.f);
+        break;
+      case VMGB_ACT_LRELU:
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = acc[i][j] > 0.f ? acc[i][j] : acc[i][j] * p.alpha;
+        break;
+      case VMGB_ACT_GELU:
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.5f * acc[i][j] * (1.f + erff(acc[i][j] * 0.70710678118654752440f));
+        break;
+      case VMGB_ACT_SIGMOID:
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 1.f / (1.f + expf(-acc[i][j]));
+        break;
+      default: break;
+    }
+  }
   const int Cout = p.Cout_g * p.groups;
   const int ncol0 = n0 + tx * 4;
 #pragma unroll
@@ -144,8 +181,7 @@ __global__ void __launch_bounds__(256) conv_generic_kernel(ConvP p) {
       const int ng = ncol0 + j;
       if (ng >= p.Cout_g) continue;
       const int co = g * p.Cout_g + ng;
-      float v = acc[i][j] + (p.bias ? p.bias[co] : 0.f);
-      v = apply_act(v, p.act, p.alpha) * p.out_scale;
+      float v = acc[i][j] * p.out_scale;
       int oc = co;
       if (p.ps == 2) {
         oc = co >> 2;

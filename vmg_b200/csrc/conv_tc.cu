@@ -222,10 +222,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int co0 = g * p.Cout_g + nb;
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float t = __uint_as_float(raw[j]);
-          if (p.bias && j < nvalid) t += __ldg(p.bias + co0 + j);
-          v[j] = apply_act(t, p.act, p.alpha) * p.out_scale;
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+        if (p.bias) {
+          if (nvalid == 16) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co0) + q);
+              v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (j < nvalid) v[j] += __ldg(p.bias + co0 + j);
+          }
+        }
+        // one warp-uniform switch per chunk (a per-element switch compiles to 16 jump-table branches)
+        switch (p.act) {
+          case VMGB_ACT_RELU:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            break;
+          case VMGB_ACT_LRELU:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.alpha;
+            break;
+          case VMGB_ACT_GELU:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
+            break;
+          case VMGB_ACT_SIGMOID:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+            break;
+          default: break;
+        }
+        if (p.out_scale != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= p.out_scale;
         }
         if (p.ps == 2) {
           // co = 4*c + 2*dy + dx  ->  out[(img, 2h+dy, 2w+dx), c]; 16 columns = 4 channels x 4 sub-pixels

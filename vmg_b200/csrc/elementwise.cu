@@ -30,6 +30,64 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* x, int x_dt,
   for (int i = 0; i < MAXV; ++i) { const int c = lane + 32 * i; if (c < C) stf(out, out_dt, base + c, (v[i] - mean) * rstd * gamma[c] + beta[c]); }
 }
 
+// vectorised variants: lane owns channels [4*lane + 128*i, +4), C % 4 == 0, C <= 1024
+constexpr int MAXQ = 8;
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const void* x, int x_dt, void* out, int out_dt,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 v[MAXQ];
+  const long long base = row * C;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i) {
+    const int c = 4 * lane + 128 * i;
+    v[i] = c < C ? ld4(x, x_dt, base + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i) {
+    if (4 * lane + 128 * i < C) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c2 = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c2 * c2 + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i) {
+    const int c = 4 * lane + 128 * i;
+    if (c < C) {
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+      st4(out, out_dt, base + c, make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                                             (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) l2norm_vec_kernel(const void* x, int x_dt, int x_pitch, void* out, int out_dt, long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 v[MAXQ];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i) {
+    const int c = 4 * lane + 128 * i;
+    v[i] = c < C ? ld4(x, x_dt, row * x_pitch + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float inv = 1.f / fmaxf(sqrtf(warp_sum(s)), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i) {
+    const int c = 4 * lane + 128 * i;
+    if (c < C) st4(out, out_dt, row * C + c, make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv));
+  }
+}
+
 // L2 normalise (F.normalize, eps 1e-12)
 __global__ void __launch_bounds__(256) l2norm_kernel(const void* x, int x_dt, int x_pitch, void* out, int out_dt,
                                                      long long rows, int C) {
@@ -142,6 +200,33 @@ __global__ void mix3_kernel(const void* h, const void* w, const void* c, int dt,
     const int b = (int)((row / rows_per_b) % B);
     const float* ab = a + (long long)b * 3 * C + ch;
     stf(out, out_dt, i, ldf(h, dt, i) * ab[0] + ldf(w, dt, i) * ab[C] + ldf(c, dt, i) * ab[2 * C]);
+  }
+}
+
+__global__ void mix3_vec_kernel(const void* h, const void* w, const void* c, int dt, const float* __restrict__ a, void* out, int out_dt,
+                                int B, long long rows_per_b, int C4, long long total4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    const long long row = i / C4;
+    const int b = (int)((row / rows_per_b) % B);
+    const float* ab = a + (long long)b * 12 * C4 + 4 * c4;
+    const float4 a0 = *reinterpret_cast<const float4*>(ab), a1 = *reinterpret_cast<const float4*>(ab + 4 * C4),
+                 a2 = *reinterpret_cast<const float4*>(ab + 8 * C4);
+    const float4 hv = ld4(h, dt, i * 4), wv = ld4(w, dt, i * 4), cv = ld4(c, dt, i * 4);
+    st4(out, out_dt, i * 4, make_float4(hv.x * a0.x + wv.x * a1.x + cv.x * a2.x, hv.y * a0.y + wv.y * a1.y + cv.y * a2.y,
+                                        hv.z * a0.z + wv.z * a1.z + cv.z * a2.z, hv.w * a0.w + wv.w * a1.w + cv.w * a2.w));
+  }
+}
+
+__global__ void ca_apply_vec_kernel(const void* u, const void* x, int dt, const float* __restrict__ y, void* out, int out_dt,
+                                    long long rows_per_frame, int C4, float scale, long long total4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    const long long fr = (i / C4) / rows_per_frame;
+    const float4 yv = *reinterpret_cast<const float4*>(y + (fr * C4 + c4) * 4);
+    const float4 uv = ld4(u, dt, i * 4), xv = ld4(x, dt, i * 4);
+    st4(out, out_dt, i * 4, make_float4((uv.x * yv.x + xv.x) * scale, (uv.y * yv.y + xv.y) * scale, (uv.z * yv.z + xv.z) * scale,
+                                        (uv.w * yv.w + xv.w) * scale));
   }
 }
 
@@ -262,6 +347,9 @@ extern "C" int vmgb_layernorm(const void* x, int x_dt, void* out, int out_dt, co
                               long long rows, int C, float eps, void* stream) {
   if (!x || !out || !gamma || !beta || !dt_ok(x_dt) || !dt_ok(out_dt) || C <= 0 || C > 32 * MAXV || rows <= 0) return VMGB_EINVAL;
   long long blocks = (rows + 7) / 8;
+  const bool vec = (C & 3) == 0 && !((uintptr_t)x & 15) && !((uintptr_t)out & 15) && !((uintptr_t)gamma & 15) && !((uintptr_t)beta & 15);
+  if (vec) layernorm_vec_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, x_dt, out, out_dt, (const float*)gamma, (const float*)beta, rows, C, eps);
+  else
   layernorm_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, x_dt, out, out_dt, (const float*)gamma, (const float*)beta, rows, C, eps);
   return check_launch();
 }
@@ -269,6 +357,9 @@ extern "C" int vmgb_layernorm(const void* x, int x_dt, void* out, int out_dt, co
 extern "C" int vmgb_l2norm(const void* x, int x_dt, int x_pitch, void* out, int out_dt, long long rows, int C, void* stream) {
   if (!x || !out || !dt_ok(x_dt) || !dt_ok(out_dt) || C <= 0 || C > 32 * MAXV || rows <= 0) return VMGB_EINVAL;
   long long blocks = (rows + 7) / 8;
+  const bool vec = (C & 3) == 0 && (x_pitch & 3) == 0 && !((uintptr_t)x & 15) && !((uintptr_t)out & 15);
+  if (vec) l2norm_vec_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, x_dt, x_pitch, out, out_dt, rows, C);
+  else
   l2norm_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, x_dt, x_pitch, out, out_dt, rows, C);
   return check_launch();
 }
@@ -310,6 +401,9 @@ extern "C" int vmgb_mix3(const void* h, const void* w, const void* c, int dt, co
                          int B, long long seg_rows, int C, void* stream) {
   if (!h || !w || !c || !a || !out || !dt_ok(dt) || !dt_ok(out_dt) || n_seg <= 0 || B <= 0) return VMGB_EINVAL;
   long long total = (long long)n_seg * B * seg_rows * C;
+  if ((C & 3) == 0 && !(((uintptr_t)h | (uintptr_t)w | (uintptr_t)c | (uintptr_t)out | (uintptr_t)a) & 15))
+    mix3_vec_kernel<<<grid_for(total / 4, 256, 148 * 32), 256, 0, as_stream(stream)>>>(h, w, c, dt, a, out, out_dt, B, seg_rows, C / 4, total / 4);
+  else
   mix3_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(h, w, c, dt, a, out, out_dt, B, seg_rows, C, total);
   return check_launch();
 }
@@ -318,6 +412,9 @@ extern "C" int vmgb_ca_apply(const void* u, const void* x, int dt, const float* 
                              long long rows_per_frame, int C, float scale, void* stream) {
   if (!u || !x || !y || !out || !dt_ok(dt) || !dt_ok(out_dt)) return VMGB_EINVAL;
   long long total = (long long)frames * rows_per_frame * C;
+  if ((C & 3) == 0 && !(((uintptr_t)u | (uintptr_t)x | (uintptr_t)y | (uintptr_t)out) & 15))
+    ca_apply_vec_kernel<<<grid_for(total / 4, 256, 148 * 32), 256, 0, as_stream(stream)>>>(u, x, dt, y, out, out_dt, rows_per_frame, C / 4, scale, total / 4);
+  else
   ca_apply_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(u, x, dt, y, out, out_dt, rows_per_frame, C, scale, total);
   return check_launch();
 }
