@@ -22,7 +22,7 @@ def close(a, b, tol):
     assert err <= tol, f'max-abs {err} > {tol}'
 
 
-def conv_case(N, H, W, Cin, Cout, R, groups, dtype, tc, n_src=1, act=ops.ACT_NONE, epi=ops.EPI_STORE, ps=0, seed=0, out_dtype=None):
+def conv_case(N, H, W, Cin, Cout, R, groups, dtype, tc, n_src=1, act=ops.ACT_NONE, epi=ops.EPI_STORE, ps=0, seed=0, out_dtype=None, variant=0):
     w = rnd(Cout, Cin // groups, R, R, seed=seed + 1, scale=(Cin // groups * R * R) ** -0.5)
     b = rnd(Cout, seed=seed + 2, scale=0.5)
     xs = [rnd(N, H, W, Cin // n_src, seed=seed + 10 + i) for i in range(n_src)]
@@ -36,7 +36,7 @@ def conv_case(N, H, W, Cin, Cout, R, groups, dtype, tc, n_src=1, act=ops.ACT_NON
     ref = emu.conv2d(tuple(xs) if n_src > 1 else xs[0], emu.pack_conv(w, b, groups), res=res, aux=aux, **kw)
     pc = ops.pack_conv(w.to(DEV), b.to(DEV), groups, tc=tc)
     dx = tuple(x.to(DEV) for x in xs) if n_src > 1 else xs[0].to(DEV)
-    out = ops.conv2d(dx, pc, res=None if res is None else res.to(DEV), aux=None if aux is None else aux.to(DEV), use_tc=tc, **kw)
+    out = ops.conv2d(dx, pc, res=None if res is None else res.to(DEV), aux=None if aux is None else aux.to(DEV), use_tc=tc, tc_variant=variant, **kw)
     torch.cuda.synchronize()
     return out, ref
 
@@ -82,6 +82,34 @@ TC = [c for c in GENERIC if c[3] >= 16] + [
 def test_conv_tcgen05(case):
     N, H, W, Cin, Cout, R, groups, act, epi, ps, n_src = case
     out, ref = conv_case(N, H, W, Cin, Cout, R, groups, torch.bfloat16, True, n_src, act, epi, ps, out_dtype=torch.float32)
+    close(out, ref, 2e-3)
+
+
+C3 = [
+    (1, 16, 16, 144, 144, 3, 1, ops.ACT_RELU, ops.EPI_RESADD, 0, 1),
+    (1, 12, 20, 112, 672, 3, 4, ops.ACT_GELU, ops.EPI_STORE, 0, 1),     # grouped, Cin_g = 28 (alignment shift)
+    (2, 6, 10, 64, 256, 3, 1, ops.ACT_LRELU, ops.EPI_STORE, 2, 1),      # pixel shuffle, NT = 256
+    (1, 10, 12, 288, 144, 3, 1, ops.ACT_LRELU, ops.EPI_STORE, 0, 2),    # virtual concat of 2
+    (1, 20, 20, 64, 3, 3, 1, ops.ACT_NONE, ops.EPI_STORE, 0, 1),
+    (1, 23, 37, 112, 112, 3, 1, ops.ACT_NONE, ops.EPI_RESADD, 0, 1),    # ragged edges
+    (1, 40, 24, 112, 112, 3, 1, ops.ACT_RELU, ops.EPI_RESADD, 0, 1),
+    (2, 17, 9, 224, 112, 3, 1, ops.ACT_LRELU, ops.EPI_STORE, 0, 2),
+    (1, 16, 16, 224, 1344, 3, 4, ops.ACT_GELU, ops.EPI_STORE, 0, 1),    # grouped, 2 N tiles
+    (4, 16, 16, 144, 576, 3, 1, ops.ACT_LRELU, ops.EPI_STORE, 2, 1),    # 3 N tiles + pixel shuffle
+    (3, 64, 48, 112, 112, 3, 1, ops.ACT_NONE, ops.EPI_RESADD, 0, 1),    # several tiles per CTA: ring wrap-around
+]
+
+
+@pytest.mark.parametrize('variant', [1, 2, 3, 6, 7], ids=['per_tap', '3x3_nsub1', '3x3_nsub2', '3x3_nsub1_cluster2', '3x3_nsub2_cluster2'])
+@pytest.mark.parametrize('case', C3, ids=lambda c: 'x'.join(map(str, c)))
+def test_conv3x3_variants(case, variant):
+    N, H, W, Cin, Cout, R, groups, act, epi, ps, n_src = case
+    cg = Cout // groups
+    nt = -(-cg // 256)
+    NT = -(-(-(-cg // nt)) // 16) * 16
+    if (variant & 3) == 3 and 2 * NT > 256:
+        pytest.skip('two sub-tiles need 2*NT <= 256 TMEM columns per accumulator set')
+    out, ref = conv_case(N, H, W, Cin, Cout, R, groups, torch.bfloat16, True, n_src, act, epi, ps, out_dtype=torch.float32, variant=variant)
     close(out, ref, 2e-3)
 
 

@@ -38,6 +38,7 @@ def conv_cases():
         ('traj_res_112_store', 1, 184, 320, 112, 112, 3, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
         ('traj_res_144', 1, 184, 320, 144, 144, 3, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
         ('traj_in_224to112', 1, 184, 320, 224, 112, 3, 1, 2, ops.EPI_STORE, ops.ACT_LRELU, 0),
+        ('traj_res_112_b2', 2, 184, 320, 112, 112, 3, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
         ('traj_res_112_b4', 4, 184, 320, 112, 112, 3, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
         ('ffn_fc1_g4_112', 25, 184, 320, 112, 672, 3, 4, 1, ops.EPI_STORE, ops.ACT_GELU, 0),
         ('ffn_fc2_672to112', 1, 1, 25 * 184 * 320, 672, 112, 1, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
@@ -51,7 +52,7 @@ def conv_cases():
     ]
 
 
-def run_conv(iters, only=None):
+def run_conv(iters, only=None, variants=(0,)):
     flush = torch.zeros(64 * 1024 * 1024, device=DEV)      # 256 MB > L2
     out = []
     for name, N, H, W, Cin, Cout, R, groups, n_src, epi, act, ps in conv_cases():
@@ -64,12 +65,19 @@ def run_conv(iters, only=None):
         oshape = (N, 2 * H, 2 * W, Cout // 4) if ps else (N, H, W, Cout)
         o = torch.empty(oshape, device=DEV, dtype=torch.float32 if Cout == 3 else torch.bfloat16)
         res = torch.randn(oshape, device=DEV).bfloat16() if epi != ops.EPI_STORE else None
-        fn = lambda: ops.conv2d(xs if n_src > 1 else xs[0], pc, act=act, alpha=0.1, epi=epi, res=res, res_scale=0.1, pixel_shuffle=ps, out=o)
-        ms = timeit(fn, iters, flush)
-        fl = 2.0 * N * H * W * Cout * R * R * (Cin // groups)
-        rec = {'case': name, 'ms': round(ms, 4), 'tflops': round(fl / ms / 1e9, 1), 'gflop': round(fl / 1e9, 2)}
-        print(json.dumps(rec), flush=True)
-        out.append(rec)
+        for variant in variants:
+            if variant > 1 and R != 3:
+                continue
+            fn = lambda: ops.conv2d(xs if n_src > 1 else xs[0], pc, act=act, alpha=0.1, epi=epi, res=res, res_scale=0.1, pixel_shuffle=ps, out=o, tc_variant=variant)
+            try:
+                ms = timeit(fn, iters, flush)
+            except RuntimeError as e:
+                print(json.dumps({'case': name, 'variant': variant, 'error': str(e)[:80]}), flush=True)
+                continue
+            fl = 2.0 * N * H * W * Cout * R * R * (Cin // groups)
+            rec = {'case': name, 'variant': variant, 'ms': round(ms, 4), 'tflops': round(fl / ms / 1e9, 1), 'gflop': round(fl / 1e9, 2)}
+            print(json.dumps(rec), flush=True)
+            out.append(rec)
     return out
 
 
@@ -113,8 +121,9 @@ if __name__ == '__main__':
     ap.add_argument('what', nargs='?', default='all')
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--only', default=None)
+    ap.add_argument('--variants', default='0')
     a = ap.parse_args()
     if a.what in ('conv', 'all'):
-        run_conv(a.iters, a.only)
+        run_conv(a.iters, a.only, tuple(int(v) for v in a.variants.split(',')))
     if a.what in ('rows', 'all'):
         run_rows(a.iters)

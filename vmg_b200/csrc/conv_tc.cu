@@ -28,6 +28,7 @@ struct TcP {
   int out_dt, out_pitch, res_dt, res_pitch, aux_dt, aux_pitch;
   int act; float alpha, out_scale; int epi; float res_scale; int ps;
   int b_stage_bytes;
+  int nsub, ra, rb, a_unit_bytes, a_sbo;       // 3x3 kernel (conv3x3_tc_kernel) only
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -74,6 +75,19 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -88,6 +102,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// same, with an explicit stride between 8-row groups (multiple of 1024 B)
+__device__ __forceinline__ uint64_t smem_desc_sw128_sbo(uint32_t addr, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
 // SWIZZLE_128B, K-major operand: 8-row groups 1024 B apart (SBO), LBO unused (=1), descriptor version 1
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
@@ -97,6 +116,107 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
 constexpr int A_STAGE_BYTES = 128 * 128;   // 128 pixels x 64 bf16
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;            // column offset of the second accumulator
+
+// ---------------------------------------------------------------------------------------------
+// epilogue of one 16-column accumulator chunk of one output pixel (thread = pixel row of the tile)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw, bool pvalid, int img, int hh, int ww,
+                                               long long pix, int g, int nt, int ch) {
+  do {
+        const int nb = nt * p.NT + ch * 16;            // first column of the chunk inside the group
+        if (!pvalid || nb >= p.Cout_g) break;
+        const int nvalid = min(16, p.Cout_g - nb);
+        const int co0 = g * p.Cout_g + nb;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+        if (p.bias) {
+          if (nvalid == 16) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co0) + q);
+              v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (j < nvalid) v[j] += __ldg(p.bias + co0 + j);
+          }
+        }
+        // one warp-uniform switch per chunk (a per-element switch compiles to 16 jump-table branches)
+        switch (p.act) {
+          case VMGB_ACT_RELU:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            break;
+          case VMGB_ACT_LRELU:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.alpha;
+            break;
+          case VMGB_ACT_GELU:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
+            break;
+          case VMGB_ACT_SIGMOID:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+            break;
+          default: break;
+        }
+        if (p.out_scale != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= p.out_scale;
+        }
+        if (p.ps == 2) {
+          // co = 4*c + 2*dy + dx  ->  out[(img, 2h+dy, 2w+dx), c]; 16 columns = 4 channels x 4 sub-pixels
+          const int c0 = co0 >> 2;
+#pragma unroll
+          for (int sp = 0; sp < 4; ++sp) {
+            const long long op = ((long long)img * (2 * p.H) + (2 * hh + (sp >> 1))) * (2 * p.W) + (2 * ww + (sp & 1));
+            if (nvalid == 16) st4(p.out, p.out_dt, op * p.out_pitch + c0, make_float4(v[sp], v[4 + sp], v[8 + sp], v[12 + sp]));
+            else
+              for (int q = 0; q < 4; ++q) if (4 * q + sp < nvalid) stf(p.out, p.out_dt, op * p.out_pitch + c0 + q, v[4 * q + sp]);
+          }
+          break;
+        }
+        const long long ob = pix * p.out_pitch + co0;
+        const bool vec = nvalid == 16 && ((p.out_pitch | co0) & 3) == 0;
+        if (p.epi != VMGB_EPI_STORE) {
+          const long long rb = pix * p.res_pitch + co0;
+          const bool rvec = nvalid == 16 && ((p.res_pitch | co0) & 3) == 0;
+          float r[16], a[16];
+          if (rvec) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float4 t = ld4(p.res, p.res_dt, rb + 4 * q); r[4 * q] = t.x; r[4 * q + 1] = t.y; r[4 * q + 2] = t.z; r[4 * q + 3] = t.w; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = j < nvalid ? ldf(p.res, p.res_dt, rb + j) : 0.f;
+          }
+          if (p.epi == VMGB_EPI_GATE) {
+            const long long ab = pix * p.aux_pitch + co0;
+            const bool avec = nvalid == 16 && ((p.aux_pitch | co0) & 3) == 0;
+            if (avec) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { const float4 t = ld4(p.aux, p.aux_dt, ab + 4 * q); a[4 * q] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) a[j] = j < nvalid ? ldf(p.aux, p.aux_dt, ab + j) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = r[j] + p.res_scale * ((a[j] + v[j]) * tanhf(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = r[j] + p.res_scale * v[j];
+          }
+        }
+        if (vec) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) st4(p.out, p.out_dt, ob + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (j < nvalid) stf(p.out, p.out_dt, ob + j, v[j]);
+        }
+        } while (false);
+}
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1)
@@ -216,97 +336,184 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         uint32_t raw[16];
         __syncwarp();                                  // tcgen05.ld is .sync.aligned: reconverge after masked stores
         tmem_ld16(taddr + ch * 16, raw);
-        const int nb = nt * p.NT + ch * 16;            // first column of the chunk inside the group
-        if (!pvalid || nb >= p.Cout_g) continue;
-        const int nvalid = min(16, p.Cout_g - nb);
-        const int co0 = g * p.Cout_g + nb;
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-        if (p.bias) {
-          if (nvalid == 16) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co0) + q);
-              v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+        epilogue_chunk(p, raw, pvalid, img, hh, ww, pix, g, nt, ch);
+      }
+      tc_fence_before();
+      mbar_arrive(tempty0 + 8 * as);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 convolution, traffic-reduced variant.  The per-tap kernel above re-reads the activation tile 9x
+// from L2; on B200 that (not the tensor pipe) bounds a 3x3 conv with C ~ 112..144.  Here a tile is
+// 16 rows x (8*nsub) columns of one image and the activation operand is loaded as "A units":
+//     unit (src, kb, s) = one TMA box {64 ch, 8*nsub cols, 18 rows} starting at column w0+s-1, row h0-1
+// One unit serves the three taps (r = 0,1,2 ; same column shift s) of both sub-tiles: the 128 rows of
+// the MMA for tap row r / sub-tile u start at byte (r*8*nsub + 8u)*128 of the unit -- a multiple of 1024,
+// so the canonical SWIZZLE_128B K-major descriptor applies with SBO = 8*nsub*128.  Activation L2 traffic
+// drops from 9x to 3 * 18/16 = 3.4x, and with nsub = 2 each weight box feeds two MMAs (M = 256 per CTA).
+// Rings: `ra` A units, `rb` weight boxes; accumulators: 2 (double buffer) x nsub x NT TMEM columns.
+// ---------------------------------------------------------------------------------------------
+template <bool kCluster>
+__global__ void __launch_bounds__(256, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB, const TcP p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + p.ra * p.a_unit_bytes;
+  const uint32_t bar_base = b_base + p.rb * p.b_stage_bytes;
+  const uint32_t afull0 = bar_base, aempty0 = afull0 + 8 * p.ra;
+  const uint32_t bfull0 = aempty0 + 8 * p.ra, bempty0 = bfull0 + 8 * p.rb;
+  const uint32_t tfull0 = bempty0 + 8 * p.rb, tempty0 = tfull0 + 16;
+  const uint32_t tmem_slot = tempty0 + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.ra; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
+    for (int i = 0; i < p.rb; ++i) { mbar_init(bfull0 + 8 * i, 1); mbar_init(bempty0 + 8 * i, kCluster ? 2 : 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (kCluster) cluster_sync_all();        // peer barriers are initialised before anything is multicast into them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int ncombo = p.groups * p.nt_per_g;
+  const int tw_cols = 8 * p.nsub;
+  // Work units.  Plain: unit = tile.  Cluster of 2: unit = (pair of consecutive M tiles, combo); CTA rank c takes
+  // M tile 2*pair + c (a missing odd tile becomes an all-out-of-bounds dummy so both CTAs stay in lockstep for
+  // the multicast weight ring).
+  const uint32_t crank = kCluster ? cluster_ctarank() : 0u;
+  const long long unit0 = kCluster ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long unit_step = kCluster ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  const long long n_mt = (long long)p.n_img * tiles_per_img;
+  const long long n_units = kCluster ? ((n_mt + 1) / 2) * ncombo : p.total_tiles;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int ia = 0, ib = 0; uint32_t pa = 0, pb = 0;
+    const uint32_t a_bytes = 18 * tw_cols * 128, b_bytes = p.NT * 128;
+    for (long long unit = unit0; unit < n_units; unit += unit_step) {
+      const int combo = (int)(unit % ncombo);
+      const long long mt = kCluster ? 2 * (unit / ncombo) + crank : unit / ncombo;
+      const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+      const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);     // img == n_img for a dummy tile
+      const int h0 = (rem / p.tiles_w) * 16, w0 = (rem % p.tiles_w) * tw_cols;
+      for (int src = 0; src < p.n_src; ++src) {
+        const CUtensorMap* mA = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
+        for (int kb = 0; kb < p.kb_per_src; ++kb) {
+          const int ca = (p.n_src > 1 ? 0 : ((g * p.Cin_g) & ~7)) + kb * 64;
+          for (int sft = 0; sft < 3; ++sft) {
+            mbar_wait(aempty0 + 8 * ia, pa ^ 1);
+            mbar_expect_tx(afull0 + 8 * ia, a_bytes);
+            tma_load_4d(a_base + ia * p.a_unit_bytes, mA, afull0 + 8 * ia, ca, w0 + sft - 1, h0 - 1, img);
+            if (++ia == p.ra) { ia = 0; pa ^= 1; }
+            for (int r = 0; r < 3; ++r) {
+              const int brow = (g * 9 + r * 3 + sft) * p.Cout_g + nt * p.NT;
+              mbar_wait(bempty0 + 8 * ib, pb ^ 1);
+              mbar_expect_tx(bfull0 + 8 * ib, b_bytes);
+              if (kCluster)      // each CTA fetches half of the weight box and multicasts it to both
+                tma_load_2d_mc(b_base + ib * p.b_stage_bytes + crank * (p.NT / 2) * 128, &mapB, bfull0 + 8 * ib, src * p.Cs + kb * 64,
+                               brow + (int)crank * (p.NT / 2), (uint16_t)3);
+              else
+                tma_load_2d(b_base + ib * p.b_stage_bytes, &mapB, bfull0 + 8 * ib, src * p.Cs + kb * 64, brow);
+              if (++ib == p.rb) { ib = 0; pb ^= 1; }
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (j < nvalid) v[j] += __ldg(p.bias + co0 + j);
           }
         }
-        // one warp-uniform switch per chunk (a per-element switch compiles to 16 jump-table branches)
-        switch (p.act) {
-          case VMGB_ACT_RELU:
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-            break;
-          case VMGB_ACT_LRELU:
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.alpha;
-            break;
-          case VMGB_ACT_GELU:
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
-            break;
-          case VMGB_ACT_SIGMOID:
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
-            break;
-          default: break;
-        }
-        if (p.out_scale != 1.f) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] *= p.out_scale;
-        }
-        if (p.ps == 2) {
-          // co = 4*c + 2*dy + dx  ->  out[(img, 2h+dy, 2w+dx), c]; 16 columns = 4 channels x 4 sub-pixels
-          const int c0 = co0 >> 2;
-#pragma unroll
-          for (int sp = 0; sp < 4; ++sp) {
-            const long long op = ((long long)img * (2 * p.H) + (2 * hh + (sp >> 1))) * (2 * p.W) + (2 * ww + (sp & 1));
-            if (nvalid == 16) st4(p.out, p.out_dt, op * p.out_pitch + c0, make_float4(v[sp], v[4 + sp], v[8 + sp], v[12 + sp]));
-            else
-              for (int q = 0; q < 4; ++q) if (4 * q + sp < nvalid) stf(p.out, p.out_dt, op * p.out_pitch + c0 + q, v[4 * q + sp]);
-          }
-          continue;
-        }
-        const long long ob = pix * p.out_pitch + co0;
-        const bool vec = nvalid == 16 && ((p.out_pitch | co0) & 3) == 0;
-        if (p.epi != VMGB_EPI_STORE) {
-          const long long rb = pix * p.res_pitch + co0;
-          const bool rvec = nvalid == 16 && ((p.res_pitch | co0) & 3) == 0;
-          float r[16], a[16];
-          if (rvec) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { const float4 t = ld4(p.res, p.res_dt, rb + 4 * q); r[4 * q] = t.x; r[4 * q + 1] = t.y; r[4 * q + 2] = t.z; r[4 * q + 3] = t.w; }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = j < nvalid ? ldf(p.res, p.res_dt, rb + j) : 0.f;
-          }
-          if (p.epi == VMGB_EPI_GATE) {
-            const long long ab = pix * p.aux_pitch + co0;
-            const bool avec = nvalid == 16 && ((p.aux_pitch | co0) & 3) == 0;
-            if (avec) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) { const float4 t = ld4(p.aux, p.aux_dt, ab + 4 * q); a[4 * q] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w; }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) a[j] = j < nvalid ? ldf(p.aux, p.aux_dt, ab + j) : 0.f;
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int ia = 0, ib = 0; uint32_t pa = 0, pb = 0;
+    uint32_t acc_phase0 = 0, acc_phase1 = 0;
+    int it = 0;
+    for (long long unit = unit0; unit < n_units; unit += unit_step, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = as ? acc_phase1 : acc_phase0;
+      mbar_wait(tempty0 + 8 * as, aph ^ 1);
+      if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+      const int g_mma = (int)(unit % ncombo) / p.nt_per_g;
+      const int kext = p.Cs + (p.n_src > 1 ? 0 : ((g_mma * p.Cin_g) & 7));
+      uint32_t accumulate = 0;
+      for (int src = 0; src < p.n_src; ++src) {
+        for (int kb = 0; kb < p.kb_per_src; ++kb) {
+          const int nks = min(4, (kext - kb * 64 + 15) >> 4);
+          for (int sft = 0; sft < 3; ++sft) {
+            mbar_wait(afull0 + 8 * ia, pa);
+            tc_fence_after();
+            const uint32_t a_unit = a_base + ia * p.a_unit_bytes;
+            for (int r = 0; r < 3; ++r) {
+              mbar_wait(bfull0 + 8 * ib, pb);
+              tc_fence_after();
+              const uint64_t bd = smem_desc_sw128(b_base + ib * p.b_stage_bytes);
+              for (int u = 0; u < p.nsub; ++u) {
+                const uint64_t ad = smem_desc_sw128_sbo(a_unit + (uint32_t)(r * tw_cols + 8 * u) * 128u, (uint32_t)p.a_sbo);
+                for (int ks = 0; ks < nks; ++ks)
+                  umma_f16(d_tmem + u * p.NT, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate);
+              }
+              accumulate = 1;
+              if (kCluster) umma_commit_mc(bempty0 + 8 * ib, (uint16_t)3); else umma_commit(bempty0 + 8 * ib);
+              if (++ib == p.rb) { ib = 0; pb ^= 1; }
             }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = r[j] + p.res_scale * ((a[j] + v[j]) * tanhf(v[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = r[j] + p.res_scale * v[j];
+            umma_commit(aempty0 + 8 * ia);
+            if (++ia == p.ra) { ia = 0; pa ^= 1; }
           }
         }
-        if (vec) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) st4(p.out, p.out_dt, ob + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) if (j < nvalid) stf(p.out, p.out_dt, ob + j, v[j]);
+      }
+      umma_commit(tfull0 + 8 * as);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;             // MMA row = dy*8 + dx of the sub-tile
+    uint32_t acc_phase0 = 0, acc_phase1 = 0;
+    int it = 0;
+    const int nchunks = p.NT >> 4;
+    for (long long unit = unit0; unit < n_units; unit += unit_step, ++it) {
+      const int as = it & 1;
+      const int combo = (int)(unit % ncombo);
+      const long long mt = kCluster ? 2 * (unit / ncombo) + crank : unit / ncombo;
+      const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+      const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
+      const int hh = (rem / p.tiles_w) * 16 + (row >> 3);
+      const uint32_t aph = as ? acc_phase1 : acc_phase0;
+      mbar_wait(tfull0 + 8 * as, aph);
+      if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+      tc_fence_after();
+      for (int u = 0; u < p.nsub; ++u) {
+        const int ww = (rem % p.tiles_w) * tw_cols + 8 * u + (row & 7);
+        const bool pvalid = hh < p.H && ww < p.W && img < p.n_img;
+        const long long pix = ((long long)img * p.H + hh) * p.W + ww;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_STRIDE + u * p.NT;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          uint32_t raw[16];
+          __syncwarp();
+          tmem_ld16(taddr + ch * 16, raw);
+          epilogue_chunk(p, raw, pvalid, img, hh, ww, pix, g, nt, ch);
         }
       }
       tc_fence_before();
@@ -316,6 +523,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (kCluster) cluster_sync_all();        // nobody exits while the peer can still multicast into / arrive on this CTA
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -342,7 +550,11 @@ static void tc_init() {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  if (g_smem_optin > 0) cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+  if (g_smem_optin > 0) {
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+  }
 }
 
 static bool encode_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -363,7 +575,6 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
                                    int res_pitch, const void* aux, int aux_dt, int aux_pitch, int n_img, int H, int W, int Cin,
                                    int Cout, int R, int S, int groups, int act, float act_alpha, float out_scale, int epi,
                                    float res_scale, int pixel_shuffle, int variant, void* stream) {
-  (void)variant;
   if (!x || !w || !out || !dt_ok(out_dt)) return VMGB_EINVAL;
   if (n_img <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || groups <= 0 || Cin % groups || Cout % groups) return VMGB_EINVAL;
   if (!(R & 1) || !(S & 1) || (x_pitch & 7) || (Kp & 15) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15))
@@ -382,9 +593,6 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   TcP p;
   p.n_img = n_img; p.H = H; p.W = W; p.Cin_g = Cin_g; p.Cout_g = Cout_g; p.groups = groups; p.R = R; p.S = S; p.n_src = n_src;
   p.Cs = n_src > 1 ? Cin / n_src : Cin_g;
-  if (H == 1) { p.BW = 128; p.BH = 1; }
-  else { p.BW = W >= 16 ? 16 : (W >= 8 ? 8 : 4); p.BH = 128 / p.BW; }
-  p.tiles_h = (H + p.BH - 1) / p.BH; p.tiles_w = (W + p.BW - 1) / p.BW;
   p.nt_per_g = (Cout_g + 255) / 256;
   p.NT = (((Cout_g + p.nt_per_g - 1) / p.nt_per_g) + 15) / 16 * 16;
   int max_koff = 0;
@@ -392,15 +600,40 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   if (Kp < Cin_g + max_koff) return VMGB_EINVAL;
   p.kb_per_src = (p.Cs + max_koff + 63) / 64;
   p.b_stage_bytes = (p.NT * 128 + 1023) / 1024 * 1024;
-  const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
-  const int budget = g_smem_optin - 1024 - 256;
-  p.stages = budget / stage_bytes;
-  if (p.stages > 8) p.stages = 8;
-  if (p.stages < 2) return VMGB_EUNSUPPORTED;
-  p.total_tiles = (long long)n_img * p.tiles_h * p.tiles_w * groups * p.nt_per_g;
   p.bias = (const float*)bias; p.out = out; p.res = res; p.aux = aux;
   p.out_dt = out_dt; p.out_pitch = out_pitch; p.res_dt = res_dt; p.res_pitch = res_pitch; p.aux_dt = aux_dt; p.aux_pitch = aux_pitch;
   p.act = act; p.alpha = act_alpha; p.out_scale = out_scale; p.epi = epi; p.res_scale = res_scale; p.ps = pixel_shuffle;
+  p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0;
+  const int budget = g_smem_optin - 1024 - 512;
+
+  // variant: 0 = auto, 1 = force the per-tap kernel, 2 = 3x3 kernel with nsub = 1, 3 = 3x3 kernel with nsub = 2;
+  // +4 = 2-CTA cluster with multicast weight boxes (3x3 kernel only)
+  const bool cluster = (variant & 4) != 0;
+  variant &= 3;
+  const bool use3x3 = R == 3 && S == 3 && H >= 8 && W >= 8 && variant != 1;
+  if (cluster && !use3x3) return VMGB_EINVAL;
+  if (use3x3) {
+    p.nsub = (variant == 2) ? 1 : ((2 * p.NT <= ACC_STRIDE && W > 8) ? 2 : 1);
+    if (variant == 3 && 2 * p.NT > ACC_STRIDE) return VMGB_EINVAL;
+    p.BH = 16; p.BW = 8 * p.nsub;
+    p.a_unit_bytes = 18 * p.BW * 128;            // multiple of 1024
+    p.a_sbo = p.BW * 128;
+    p.ra = 3;
+    p.rb = (budget - p.ra * p.a_unit_bytes) / p.b_stage_bytes;
+    if (p.rb > 8) p.rb = 8;
+    if (p.rb < 3) { p.ra = 2; p.rb = (budget - p.ra * p.a_unit_bytes) / p.b_stage_bytes; if (p.rb > 8) p.rb = 8; }
+    if (p.rb < 2) return VMGB_EUNSUPPORTED;
+    p.stages = 0;
+  } else {
+    if (H == 1) { p.BW = 128; p.BH = 1; }
+    else { p.BW = W >= 16 ? 16 : (W >= 8 ? 8 : 4); p.BH = 128 / p.BW; }
+    const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
+    p.stages = budget / stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    if (p.stages < 2) return VMGB_EUNSUPPORTED;
+  }
+  p.tiles_h = (H + p.BH - 1) / p.BH; p.tiles_w = (W + p.BW - 1) / p.BW;
+  p.total_tiles = (long long)n_img * p.tiles_h * p.tiles_w * groups * p.nt_per_g;
 
   // activation maps: dims (C, W, H, N) ; channel extent = the source's own channel count so that the
   // K tail and the virtual-concat boundary are zero-filled by TMA
@@ -412,17 +645,34 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
     if (reinterpret_cast<uintptr_t>(ptr) & 15) return VMGB_EINVAL;
     cuuint64_t dims[4] = {(cuuint64_t)c_extent, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
     cuuint64_t str[3] = {(cuuint64_t)x_pitch * 2, (cuuint64_t)W * x_pitch * 2, (cuuint64_t)H * W * x_pitch * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.BW, (cuuint32_t)(use3x3 ? 18 : p.BH), 1};
     if (!encode_bf16(&mA[s], ptr, 4, dims, str, box)) return VMGB_EINVAL;
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)groups * R * S * Cout_g};
     cuuint64_t str[1] = {(cuuint64_t)Kp * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)p.NT};
+    cuuint32_t box[2] = {64, (cuuint32_t)(cluster ? p.NT / 2 : p.NT)};
     if (!encode_bf16(&mB, w, 2, dims, str, box)) return VMGB_EINVAL;
   }
-  const int smem = p.stages * stage_bytes + 1024 + 256;
   const long long grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  conv_tc_kernel<<<(unsigned)grid, 256, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
+  if (use3x3 && cluster) {
+    const int smem = p.ra * p.a_unit_bytes + p.rb * p.b_stage_bytes + 1024 + 512;
+    const long long n_mt = (long long)n_img * p.tiles_h * p.tiles_w;
+    const long long units = ((n_mt + 1) / 2) * groups * p.nt_per_g;
+    long long clusters = units < g_num_sms / 2 ? units : g_num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<true>, mA[0], mA[1], mA[2], mB, p);
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return VMGB_ECUDA; }
+  } else if (use3x3) {
+    const int smem = p.ra * p.a_unit_bytes + p.rb * p.b_stage_bytes + 1024 + 512;
+    conv3x3_tc_kernel<false><<<(unsigned)grid, 256, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
+  } else {
+    const int smem = p.stages * (A_STAGE_BYTES + p.b_stage_bytes) + 1024 + 512;
+    conv_tc_kernel<<<(unsigned)grid, 256, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
+  }
   return check_launch();
 }

@@ -143,6 +143,55 @@ __global__ void morph_scatter_kernel(const void* Y, int y_dt, void* out, int out
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Morph-FC permutation, block-staged version.  For a fixed (bt, other-axis position o, chunk group lg)
+// the ch x C source elements map onto ONE contiguous run of ch x Cp destination elements
+// (rows (..)*ch + g, g = 0..ch-1), so a warp stages the block in shared memory: coalesced reads of
+// C-element pixel rows, in-smem (r, g, s) -> (g, r, s) transpose, coalesced writes.  inverse = scatter.
+// ---------------------------------------------------------------------------------------------
+constexpr int MORPH_WARPS = 4;
+__global__ void __launch_bounds__(32 * MORPH_WARPS) morph_block_kernel(const void* src, int src_dt, void* dst, int dst_dt, int BT, int H,
+                                                                      int W, int C, int ch, int axis, int inverse, long long n_blocks) {
+  extern __shared__ float sm_all[];
+  const int Cp = (C + ch - 1) / ch * ch, S = Cp / ch;
+  const int L = axis == 0 ? H : W, Lg = (L + ch - 1) / ch, O = axis == 0 ? W : H;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* sm = sm_all + wid * (ch * Cp);
+  const long long blk = (long long)blockIdx.x * (blockDim.x >> 5) + wid;
+  if (blk >= n_blocks) return;
+  // block index = (bt*O + o)*Lg + lg  (same order as the row index / ch)
+  const int lg = (int)(blk % Lg); const long long t = blk / Lg; const int o = (int)(t % O); const int bt = (int)(t / O);
+  const long long rows0 = blk * ch;                     // first A row of this block
+  if (!inverse) {
+    for (int i = lane; i < ch * Cp; i += 32) sm[i] = 0.f;
+    __syncwarp();
+    for (int i = lane; i < ch * C; i += 32) {
+      const int r = i / C, c = i - r * C;
+      const int l = lg * ch + r;
+      if (l < L) {
+        const int h = axis == 0 ? l : o, w = axis == 0 ? o : l;
+        const int g = c / S, s2 = c - g * S;
+        sm[g * Cp + r * S + s2] = ldf(src, src_dt, (((long long)bt * H + h) * W + w) * C + c);
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < ch * Cp; i += 32) stf(dst, dst_dt, rows0 * Cp + i, sm[i]);
+  } else {
+    for (int i = lane; i < ch * Cp; i += 32) sm[i] = ldf(src, src_dt, rows0 * Cp + i);
+    __syncwarp();
+    for (int i = lane; i < ch * C; i += 32) {
+      const int r = i / C, c = i - r * C;
+      const int l = lg * ch + r;
+      if (l < L) {
+        const int h = axis == 0 ? l : o, w = axis == 0 ? o : l;
+        const int g = c / S, s2 = c - g * S;
+        stf(dst, dst_dt, (((long long)bt * H + h) * W + w) * C + c, sm[g * Cp + r * S + s2]);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // grouped channel sums (atomic accumulation of per-block partials into a zeroed fp32 buffer)
 // grid = (row chunks, groups); block = 256 threads = 8 row lanes x 32 channel lanes
@@ -369,6 +418,18 @@ extern "C" int vmgb_morph_permute(const void* src, int src_dt, void* dst, int ds
   if (!src || !dst || !dt_ok(src_dt) || !dt_ok(dst_dt) || chunk <= 0 || (axis != 0 && axis != 1)) return VMGB_EINVAL;
   const int Cp = (C + chunk - 1) / chunk * chunk;
   const int L = axis == 0 ? H : W, Lp = (L + chunk - 1) / chunk * chunk, O = axis == 0 ? W : H;
+  const size_t per_warp = (size_t)chunk * Cp * sizeof(float);
+  int warps = (int)((48 * 1024) / per_warp);
+  if (warps > MORPH_WARPS) warps = MORPH_WARPS;
+  if (warps >= 1) {
+    const size_t smem = per_warp * warps;
+    const long long n_blocks = (long long)BT * O * (Lp / chunk);
+    const long long grid = (n_blocks + warps - 1) / warps;
+    if (grid > 2147483647LL) return VMGB_EINVAL;
+    morph_block_kernel<<<(unsigned)grid, 32 * warps, smem, as_stream(stream)>>>(src, src_dt, dst, dst_dt, BT, H, W, C, chunk, axis,
+                                                                                      inverse, n_blocks);
+    return check_launch();
+  }
   if (!inverse) {
     long long total = (long long)BT * Lp * O * Cp;
     morph_gather_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(src, src_dt, dst, dst_dt, BT, H, W, C, chunk, axis, total);

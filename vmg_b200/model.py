@@ -407,49 +407,52 @@ class VMG(nn.Module):
         return y
 
     def _trajectory(self, st, x, B, T, flows_f, flows_b):
+        """Both sweeps of Trajectory_multi_head share their weights and are independent until the final
+        fusion (trajectory.py:476-478 only reads outputs_back[i]), so they advance in lockstep as ONE image
+        batch: step j = [backward sweep at frame T-1-j | forward sweep at frame j].  Key frames fall on the
+        same steps (j % stride == 0) in both sweeps, so key-frame k of either sweep is step k*stride."""
         o = _ops
         tm = st.traj_mixing
         N, H, W, C = x.shape
         n = B
         xs = x.view(T, n, H, W, C)
-        qn = o.l2norm(x).view(T, n, H, W, C)            # queries; a key frame's keys are its own qn
+        qn = o.l2norm(x).view(T, n, H, W, C)            # queries; a key frame's keys are its own normalised input
+        # paired, step-major copies (pure data movement): [T, 2n, H, W, C]
+        xp = torch.stack([xs.flip(0), xs], 1).reshape(T, 2 * n, H, W, C)
+        qp = torch.stack([qn.flip(0), qn], 1).reshape(T, 2 * n, H, W, C)
+        del qn
+        # step j >= 1: backward sweep uses flows_backward[:, T-1-j], forward sweep flows_forward[:, j-1]
+        fl = torch.stack([flows_b.flip(0), flows_f], 1).reshape(T - 1, 2 * n, H, W, 2) if T > 1 else None
         stride = st.key_stride
         kcap = (T + stride - 1) // stride
-        frame_elems = n * H * W * C
+        step_elems = 2 * n * H * W * C
         proj = self._pc(tm.LTAM.proj)
         rel = tm.LTAM.relative_pos_encoding.detach().contiguous()
         decay = tm.LTAM.decay_v
-        feats = []
-        for order, keyset, flows, fidx, kstep in (
-                (range(T - 1, -1, -1), set(range(T - 1, -1, -stride)), flows_b, (lambda i: i), -stride),
-                (range(0, T), set(range(0, T, stride)), flows_f, (lambda i: i - 1), stride)):
-            fbuf = torch.empty((T, n, H, W, C), device=x.device, dtype=x.dtype)
-            loc = [torch.empty((n, H, W, 2 * kcap), device=x.device, dtype=torch.float32) for _ in range(2)]
-            o.loc_identity_(loc[0], 0)
-            cur_loc, K = 0, 0
-            prev = None
-            first_frame = None
-            for i in order:
-                if prev is None:
-                    first_frame = i
-                    feat_in = torch.zeros((n, H, W, C), device=x.device, dtype=x.dtype)
-                else:
-                    flow = flows[fidx(i)]
-                    warped = o.flow_warp_bilinear(prev, flow)
-                    o.flow_warp_nearest(loc[cur_loc], flow, 2 * K, loc[1 - cur_loc])
-                    cur_loc = 1 - cur_loc
-                    att = o.ltam_wins(qn[i], qn[first_frame], fbuf[first_frame], kstep * frame_elems, K, loc[cur_loc],
-                                      rel, decay, st.heads)
-                    feat_in = o.linear(att, proj, epi=o.EPI_RESADD, res=warped)
-                    if i in keyset:
-                        o.loc_identity_(loc[cur_loc], 2 * K)
-                if i in keyset:
-                    K += 1                              # frame i is pushed as key frame K-1 once fbuf[i] is written
-                prev = self._resblocks(tm.resblocks, (xs[i], feat_in), fbuf[i])
-            feats.append(fbuf)
-        out = o.conv2d((feats[0].view(N, H, W, C), x, feats[1].view(N, H, W, C)), self._pc(tm.fusion),
-                       act=o.ACT_LRELU, alpha=0.1)
-        return out
+        fbuf = torch.empty((T, 2 * n, H, W, C), device=x.device, dtype=x.dtype)
+        loc = [torch.empty((2 * n, H, W, 2 * kcap), device=x.device, dtype=torch.float32) for _ in range(2)]
+        o.loc_identity_(loc[0], 0)
+        cur_loc, K = 0, 0
+        prev = None
+        for j in range(T):
+            is_key = j % stride == 0
+            if j == 0:
+                feat_in = torch.zeros((2 * n, H, W, C), device=x.device, dtype=x.dtype)
+            else:
+                flow = fl[j - 1]
+                warped = o.flow_warp_bilinear(prev, flow)
+                o.flow_warp_nearest(loc[cur_loc], flow, 2 * K, loc[1 - cur_loc])
+                cur_loc = 1 - cur_loc
+                att = o.ltam_wins(qp[j], qp[0], fbuf[0], stride * step_elems, K, loc[cur_loc], rel, decay, st.heads)
+                feat_in = o.linear(att, proj, epi=o.EPI_RESADD, res=warped)
+                if is_key:
+                    o.loc_identity_(loc[cur_loc], 2 * K)
+            if is_key:
+                K += 1                                  # step j becomes key frame K-1 once fbuf[j] is written
+            prev = self._resblocks(tm.resblocks, (xp[j], feat_in), fbuf[j])
+        back = fbuf[:, :n].flip(0).reshape(N, H, W, C)  # outputs_back[i] = backward sweep at step T-1-i
+        fwd = fbuf[:, n:].reshape(N, H, W, C)
+        return o.conv2d((back, x, fwd), self._pc(tm.fusion), act=o.ACT_LRELU, alpha=0.1)
 
     # -------------------------------------------------------------------------------------------
     def _stage(self, st, x, B, T, flows):
