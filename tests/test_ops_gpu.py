@@ -100,7 +100,7 @@ C3 = [
 ]
 
 
-@pytest.mark.parametrize('variant', [1, 2, 3, 6, 7], ids=['per_tap', '3x3_nsub1', '3x3_nsub2', '3x3_nsub1_cluster2', '3x3_nsub2_cluster2'])
+@pytest.mark.parametrize('variant', [0, 1, 2, 3, 6, 7], ids=['auto', 'per_tap', '3x3_nsub1', '3x3_nsub2', '3x3_nsub1_cluster2', '3x3_nsub2_cluster2'])
 @pytest.mark.parametrize('case', C3, ids=lambda c: 'x'.join(map(str, c)))
 def test_conv3x3_variants(case, variant):
     N, H, W, Cin, Cout, R, groups, act, epi, ps, n_src = case

@@ -99,6 +99,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// one elected lane of a converged warp (keeps the surrounding code warp-uniform so that descriptors and
+// barrier addresses live in uniform registers; a `lane == 0` branch makes ptxas wrap every UTCHMMA / UTMALDG
+// in an R2UR.BROADCAST "waterfall" loop, ~4x slower issue)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -118,108 +126,180 @@ constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;            // column offset of the second accumulator
 
 // ---------------------------------------------------------------------------------------------
-// epilogue of one 16-column accumulator chunk of one output pixel (thread = pixel row of the tile)
+// Epilogue.  EPI_WARPS warps (4 or 8) drain one 128 x NT accumulator: warp w owns TMEM lanes 32*(w%4)..+31
+// (its pixel rows) and the 16-column chunks ch = w/4, w/4 + EPI_WARPS/4, ...  Per tile a thread
+//   1. prefetches the bf16 residual of all its chunks into registers BEFORE waiting for the accumulator
+//      (the loads ride under the MMA main loop; the profile of the first version showed the epilogue warps
+//      stalled on exactly these L2 round trips, one per chunk),
+//   2. reads the bias from shared memory (staged once per (group, N tile)),
+//   3. tcgen05.ld -> bias / activation / scale / residual / gate / pixel shuffle -> 16-byte stores.
 // ---------------------------------------------------------------------------------------------
+constexpr int MAX_PRE = 8;       // chunks per thread whose residual is prefetched (8 warps x 8 = NT 256 at most... x2 halves)
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 q;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  return q;
+}
+
+// whether chunk `nb` (first column inside the group) of this pixel can use the vector bf16 residual prefetch
+__device__ __forceinline__ bool pre_ok(const TcP& p, bool pvalid, int g, int nb) {
+  return pvalid && p.epi != VMGB_EPI_STORE && p.res_dt == VMGB_BF16 && p.ps == 0 && nb + 16 <= p.Cout_g &&
+         (((g * p.Cout_g + nb) | p.res_pitch) & 7) == 0;
+}
+
 __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw, bool pvalid, int img, int hh, int ww,
-                                               long long pix, int g, int nt, int ch) {
-  do {
-        const int nb = nt * p.NT + ch * 16;            // first column of the chunk inside the group
-        if (!pvalid || nb >= p.Cout_g) break;
-        const int nvalid = min(16, p.Cout_g - nb);
-        const int co0 = g * p.Cout_g + nb;
-        float v[16];
+                                               long long pix, int g, int nt, int ch, const float* bias_s, bool have_pre,
+                                               const uint4& pre0, const uint4& pre1) {
+  const int nb = nt * p.NT + ch * 16;            // first column of the chunk inside the group
+  if (!pvalid || nb >= p.Cout_g) return;
+  const int nvalid = min(16, p.Cout_g - nb);
+  const int co0 = g * p.Cout_g + nb;
+  float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-        if (p.bias) {
-          if (nvalid == 16) {
+  for (int q = 0; q < 4; ++q) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + ch * 16 + 4 * q);     // smem broadcast
+    v[4 * q] = __uint_as_float(raw[4 * q]) + b4.x; v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b4.y;
+    v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b4.z; v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b4.w;
+  }
+  // one warp-uniform switch per chunk (a per-element switch compiles to 16 jump-table branches)
+  switch (p.act) {
+    case VMGB_ACT_RELU:
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co0) + q);
-              v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
-            }
-          } else {
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      break;
+    case VMGB_ACT_LRELU:
 #pragma unroll
-            for (int j = 0; j < 16; ++j) if (j < nvalid) v[j] += __ldg(p.bias + co0 + j);
-          }
-        }
-        // one warp-uniform switch per chunk (a per-element switch compiles to 16 jump-table branches)
-        switch (p.act) {
-          case VMGB_ACT_RELU:
+      for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.alpha;
+      break;
+    case VMGB_ACT_GELU:
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-            break;
-          case VMGB_ACT_LRELU:
+      for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
+      break;
+    case VMGB_ACT_SIGMOID:
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.alpha;
-            break;
-          case VMGB_ACT_GELU:
+      for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+      break;
+    default: break;
+  }
+  if (p.out_scale != 1.f) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
-            break;
-          case VMGB_ACT_SIGMOID:
+    for (int j = 0; j < 16; ++j) v[j] *= p.out_scale;
+  }
+  if (p.ps == 2) {
+    // co = 4*c + 2*dy + dx  ->  out[(img, 2h+dy, 2w+dx), c]; 16 columns = 4 channels x 4 sub-pixels
+    const int c0 = co0 >> 2;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
-            break;
-          default: break;
-        }
-        if (p.out_scale != 1.f) {
+    for (int sp = 0; sp < 4; ++sp) {
+      const long long op = ((long long)img * (2 * p.H) + (2 * hh + (sp >> 1))) * (2 * p.W) + (2 * ww + (sp & 1));
+      if (nvalid == 16) st4(p.out, p.out_dt, op * p.out_pitch + c0, make_float4(v[sp], v[4 + sp], v[8 + sp], v[12 + sp]));
+      else
+        for (int q = 0; q < 4; ++q) if (4 * q + sp < nvalid) stf(p.out, p.out_dt, op * p.out_pitch + c0 + q, v[4 * q + sp]);
+    }
+    return;
+  }
+  const long long ob = pix * p.out_pitch + co0;
+  if (p.epi != VMGB_EPI_STORE) {
+    const long long rb = pix * p.res_pitch + co0;
+    float r[16], a[16];
+    if (have_pre) {
+      unpack8(pre0, r); unpack8(pre1, r + 8);
+    } else if (nvalid == 16 && ((p.res_pitch | co0) & 3) == 0) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] *= p.out_scale;
-        }
-        if (p.ps == 2) {
-          // co = 4*c + 2*dy + dx  ->  out[(img, 2h+dy, 2w+dx), c]; 16 columns = 4 channels x 4 sub-pixels
-          const int c0 = co0 >> 2;
+      for (int q = 0; q < 4; ++q) { const float4 t = ld4(p.res, p.res_dt, rb + 4 * q); r[4 * q] = t.x; r[4 * q + 1] = t.y; r[4 * q + 2] = t.z; r[4 * q + 3] = t.w; }
+    } else {
 #pragma unroll
-          for (int sp = 0; sp < 4; ++sp) {
-            const long long op = ((long long)img * (2 * p.H) + (2 * hh + (sp >> 1))) * (2 * p.W) + (2 * ww + (sp & 1));
-            if (nvalid == 16) st4(p.out, p.out_dt, op * p.out_pitch + c0, make_float4(v[sp], v[4 + sp], v[8 + sp], v[12 + sp]));
-            else
-              for (int q = 0; q < 4; ++q) if (4 * q + sp < nvalid) stf(p.out, p.out_dt, op * p.out_pitch + c0 + q, v[4 * q + sp]);
-          }
-          break;
-        }
-        const long long ob = pix * p.out_pitch + co0;
-        const bool vec = nvalid == 16 && ((p.out_pitch | co0) & 3) == 0;
-        if (p.epi != VMGB_EPI_STORE) {
-          const long long rb = pix * p.res_pitch + co0;
-          const bool rvec = nvalid == 16 && ((p.res_pitch | co0) & 3) == 0;
-          float r[16], a[16];
-          if (rvec) {
+      for (int j = 0; j < 16; ++j) r[j] = j < nvalid ? ldf(p.res, p.res_dt, rb + j) : 0.f;
+    }
+    if (p.epi == VMGB_EPI_GATE) {
+      const long long ab = pix * p.aux_pitch + co0;
+      if (nvalid == 16 && ((p.aux_pitch | co0) & 3) == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { const float4 t = ld4(p.res, p.res_dt, rb + 4 * q); r[4 * q] = t.x; r[4 * q + 1] = t.y; r[4 * q + 2] = t.z; r[4 * q + 3] = t.w; }
-          } else {
+        for (int q = 0; q < 4; ++q) { const float4 t = ld4(p.aux, p.aux_dt, ab + 4 * q); a[4 * q] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w; }
+      } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = j < nvalid ? ldf(p.res, p.res_dt, rb + j) : 0.f;
-          }
-          if (p.epi == VMGB_EPI_GATE) {
-            const long long ab = pix * p.aux_pitch + co0;
-            const bool avec = nvalid == 16 && ((p.aux_pitch | co0) & 3) == 0;
-            if (avec) {
+        for (int j = 0; j < 16; ++j) a[j] = j < nvalid ? ldf(p.aux, p.aux_dt, ab + j) : 0.f;
+      }
 #pragma unroll
-              for (int q = 0; q < 4; ++q) { const float4 t = ld4(p.aux, p.aux_dt, ab + 4 * q); a[4 * q] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w; }
-            } else {
+      for (int j = 0; j < 16; ++j) v[j] = r[j] + p.res_scale * ((a[j] + v[j]) * tanhf(v[j]));
+    } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) a[j] = j < nvalid ? ldf(p.aux, p.aux_dt, ab + j) : 0.f;
-            }
+      for (int j = 0; j < 16; ++j) v[j] = r[j] + p.res_scale * v[j];
+    }
+  }
+  if (nvalid == 16 && p.out_dt == VMGB_BF16 && ((p.out_pitch | co0) & 7) == 0) {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ob);
+    o[0] = pack8(v); o[1] = pack8(v + 8);
+  } else if (nvalid == 16 && ((p.out_pitch | co0) & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = r[j] + p.res_scale * ((a[j] + v[j]) * tanhf(v[j]));
-          } else {
+    for (int q = 0; q < 4; ++q) st4(p.out, p.out_dt, ob + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+  } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = r[j] + p.res_scale * v[j];
-          }
-        }
-        if (vec) {
+    for (int j = 0; j < 16; ++j) if (j < nvalid) stf(p.out, p.out_dt, ob + j, v[j]);
+  }
+}
+
+// One accumulator (sub-tile) of one tile, executed by all EPI_WARPS epilogue warps.
+//   ew: epilogue warp index 0..EPI_WARPS-1 ; lane quarter = ew & 3 ; chunk phase = ew >> 2
+template <int EPI_WARPS>
+__device__ __forceinline__ void epilogue_tile(const TcP& p, float* bias_s, int& bias_combo, int combo, int ew, int lane, uint32_t tmem_acc,
+                                              int img, int hh, int ww, bool pvalid, int g, int nt, uint32_t tfull_bar, uint32_t parity,
+                                              bool wait_full) {
+  constexpr int STEP = EPI_WARPS / 4;
+  const int nchunks = p.NT >> 4;
+  const int half = ew >> 2;
+  const long long pix = ((long long)img * p.H + hh) * p.W + ww;
+  // 1. residual prefetch (registers), issued before the accumulator is complete
+  uint4 pre[MAX_PRE][2];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) st4(p.out, p.out_dt, ob + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-        } else {
+  for (int i = 0; i < MAX_PRE; ++i) {
+    const int ch = half + STEP * i;
+    pre[i][0] = make_uint4(0, 0, 0, 0); pre[i][1] = make_uint4(0, 0, 0, 0);
+    if (ch < nchunks && pre_ok(p, pvalid, g, nt * p.NT + ch * 16)) {
+      const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_pitch + g * p.Cout_g + nt * p.NT + ch * 16;
+      pre[i][0] = ldg_nc_v4(rp); pre[i][1] = ldg_nc_v4(rp + 8);
+    }
+  }
+  // 2. bias of this (group, N tile) -> smem, once per change of combo
+  if (combo != bias_combo) {
+    asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");          // previous readers are done
+    const int t = ew * 32 + lane;
+    for (int c = t; c < p.NT; c += EPI_WARPS * 32) {
+      const int nb = nt * p.NT + c;
+      bias_s[c] = (p.bias && nb < p.Cout_g) ? __ldg(p.bias + g * p.Cout_g + nb) : 0.f;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+    bias_combo = combo;
+  }
+  if (wait_full) { mbar_wait(tfull_bar, parity); tc_fence_after(); }
+  // 3. drain
 #pragma unroll
-          for (int j = 0; j < 16; ++j) if (j < nvalid) stf(p.out, p.out_dt, ob + j, v[j]);
-        }
-        } while (false);
+  for (int i = 0; i < 16 / STEP; ++i) {
+    const int ch = half + STEP * i;
+    if (ch >= nchunks) break;
+    uint32_t raw[16];
+    __syncwarp();
+    tmem_ld16(tmem_acc + ch * 16, raw);
+    const bool hp = i < MAX_PRE && pre_ok(p, pvalid, g, nt * p.NT + ch * 16);
+    epilogue_chunk(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, pre[i < MAX_PRE ? i : 0][0], pre[i < MAX_PRE ? i : 0][1]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1)
+constexpr int TC_THREADS = 384;      // warps 0-3: producer / MMA / TMEM alloc / spare ; warps 4-11: epilogue
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB, const TcP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -233,10 +313,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const uint32_t tmem_slot = tempty0 + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -249,14 +329,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));   // NT floats after the barriers
 
   const int taps = p.R * p.S;
   const int kblocks = taps * p.n_src * p.kb_per_src;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   const int ncombo = p.groups * p.nt_per_g;
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp runs the loops, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
     const uint32_t tx_bytes = A_STAGE_BYTES + p.NT * 128;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -271,19 +352,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           const CUtensorMap* mA = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
           for (int kb = 0; kb < p.kb_per_src; ++kb) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            mbar_expect_tx(full0 + 8 * stage, tx_bytes);
             // grouped conv: start the box at a 16-byte aligned channel; the packed weights of the group are
             // shifted by the same `koff` rows of zeros (vmgb_pack_weight_tc)
             const int ca = (p.n_src > 1 ? 0 : ((g * p.Cin_g) & ~7)) + kb * 64;
-            tma_load_4d(a_base + stage * A_STAGE_BYTES, mA, full0 + 8 * stage, ca, w0 + dw, h0 + dh, img);
-            tma_load_2d(b_base + stage * p.b_stage_bytes, &mapB, full0 + 8 * stage, src * p.Cs + kb * 64, brow);
+            if (elect_one()) {
+              mbar_expect_tx(full0 + 8 * stage, tx_bytes);
+              tma_load_4d(a_base + stage * A_STAGE_BYTES, mA, full0 + 8 * stage, ca, w0 + dw, h0 + dh, img);
+              tma_load_2d(b_base + stage * p.b_stage_bytes, &mapB, full0 + 8 * stage, src * p.Cs + kb * 64, brow);
+            }
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp runs the loops, one elected lane issues) =====================
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int stage = 0; uint32_t phase = 0;
     uint32_t acc_phase[2] = {0, 0};
@@ -304,22 +388,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tc_fence_after();
         const uint64_t ad = smem_desc_sw128(a_base + stage * A_STAGE_BYTES);
         const uint64_t bd = smem_desc_sw128(b_base + stage * p.b_stage_bytes);
-        for (int ks = 0; ks < nks; ++ks) {
-          umma_f16(d_tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate);   // +32 B per K step
-          accumulate = 1;
+        if (elect_one()) {
+          for (int ks = 0; ks < nks; ++ks)      // +32 B per K step; the very first K step of the tile overwrites
+            umma_f16(d_tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)(ks > 0));
+          umma_commit(empty0 + 8 * stage);
+          if (kbi == kblocks - 1) umma_commit(tfull0 + 8 * as);
         }
-        umma_commit(empty0 + 8 * stage);
+        __syncwarp();
+        accumulate = 1;
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull0 + 8 * as);
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int quarter = warp & 3;
+    // ===================== epilogue (8 warps) =====================
+    const int ew = warp - 4, quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    uint32_t acc_phase[2] = {0, 0};
-    int it = 0;
-    const int nchunks = p.NT >> 4;
+    uint32_t acc_phase0 = 0, acc_phase1 = 0;
+    int it = 0, bias_combo = -1;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const int combo = (int)(tile % ncombo); const long long mt = tile / ncombo;
@@ -327,17 +412,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
       const int hh = (rem / p.tiles_w) * p.BH + row / p.BW, ww = (rem % p.tiles_w) * p.BW + row % p.BW;
       const bool pvalid = hh < p.H && ww < p.W;
-      const long long pix = ((long long)img * p.H + hh) * p.W + ww;
-      mbar_wait(tfull0 + 8 * as, acc_phase[as]);
-      acc_phase[as] ^= 1;
-      tc_fence_after();
+      const uint32_t aph = as ? acc_phase1 : acc_phase0;
+      if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_STRIDE;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        uint32_t raw[16];
-        __syncwarp();                                  // tcgen05.ld is .sync.aligned: reconverge after masked stores
-        tmem_ld16(taddr + ch * 16, raw);
-        epilogue_chunk(p, raw, pvalid, img, hh, ww, pix, g, nt, ch);
-      }
+      epilogue_tile<8>(p, bias_s, bias_combo, combo, ew, lane, taddr, img, hh, ww, pvalid, g, nt, tfull0 + 8 * as, aph, true);
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * as);
     }
@@ -378,7 +456,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const uint32_t tmem_slot = tempty0 + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.ra; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
     for (int i = 0; i < p.rb; ++i) { mbar_init(bfull0 + 8 * i, 1); mbar_init(bempty0 + 8 * i, kCluster ? 2 : 1); }
@@ -409,8 +487,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const long long n_mt = (long long)p.n_img * tiles_per_img;
   const long long n_units = kCluster ? ((n_mt + 1) / 2) * ncombo : p.total_tiles;
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp runs the loops, one elected lane issues) =====================
     int ia = 0, ib = 0; uint32_t pa = 0, pb = 0;
     const uint32_t a_bytes = 18 * tw_cols * 128, b_bytes = p.NT * 128;
     for (long long unit = unit0; unit < n_units; unit += unit_step) {
@@ -425,26 +503,32 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           const int ca = (p.n_src > 1 ? 0 : ((g * p.Cin_g) & ~7)) + kb * 64;
           for (int sft = 0; sft < 3; ++sft) {
             mbar_wait(aempty0 + 8 * ia, pa ^ 1);
-            mbar_expect_tx(afull0 + 8 * ia, a_bytes);
-            tma_load_4d(a_base + ia * p.a_unit_bytes, mA, afull0 + 8 * ia, ca, w0 + sft - 1, h0 - 1, img);
+            if (elect_one()) {
+              mbar_expect_tx(afull0 + 8 * ia, a_bytes);
+              tma_load_4d(a_base + ia * p.a_unit_bytes, mA, afull0 + 8 * ia, ca, w0 + sft - 1, h0 - 1, img);
+            }
+            __syncwarp();
             if (++ia == p.ra) { ia = 0; pa ^= 1; }
             for (int r = 0; r < 3; ++r) {
               const int brow = (g * 9 + r * 3 + sft) * p.Cout_g + nt * p.NT;
               mbar_wait(bempty0 + 8 * ib, pb ^ 1);
-              mbar_expect_tx(bfull0 + 8 * ib, b_bytes);
-              if (kCluster)      // each CTA fetches half of the weight box and multicasts it to both
-                tma_load_2d_mc(b_base + ib * p.b_stage_bytes + crank * (p.NT / 2) * 128, &mapB, bfull0 + 8 * ib, src * p.Cs + kb * 64,
-                               brow + (int)crank * (p.NT / 2), (uint16_t)3);
-              else
-                tma_load_2d(b_base + ib * p.b_stage_bytes, &mapB, bfull0 + 8 * ib, src * p.Cs + kb * 64, brow);
+              if (elect_one()) {
+                mbar_expect_tx(bfull0 + 8 * ib, b_bytes);
+                if (kCluster)      // each CTA fetches half of the weight box and multicasts it to both
+                  tma_load_2d_mc(b_base + ib * p.b_stage_bytes + crank * (p.NT / 2) * 128, &mapB, bfull0 + 8 * ib, src * p.Cs + kb * 64,
+                                 brow + (int)crank * (p.NT / 2), (uint16_t)3);
+                else
+                  tma_load_2d(b_base + ib * p.b_stage_bytes, &mapB, bfull0 + 8 * ib, src * p.Cs + kb * 64, brow);
+              }
+              __syncwarp();
               if (++ib == p.rb) { ib = 0; pb ^= 1; }
             }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp runs the loops, one elected lane issues) =====================
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int ia = 0, ib = 0; uint32_t pa = 0, pb = 0;
     uint32_t acc_phase0 = 0, acc_phase1 = 0;
@@ -470,29 +554,33 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               mbar_wait(bfull0 + 8 * ib, pb);
               tc_fence_after();
               const uint64_t bd = smem_desc_sw128(b_base + ib * p.b_stage_bytes);
-              for (int u = 0; u < p.nsub; ++u) {
-                const uint64_t ad = smem_desc_sw128_sbo(a_unit + (uint32_t)(r * tw_cols + 8 * u) * 128u, (uint32_t)p.a_sbo);
-                for (int ks = 0; ks < nks; ++ks)
-                  umma_f16(d_tmem + u * p.NT, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate);
+              if (elect_one()) {
+                for (int u = 0; u < p.nsub; ++u) {
+                  const uint64_t ad = smem_desc_sw128_sbo(a_unit + (uint32_t)(r * tw_cols + 8 * u) * 128u, (uint32_t)p.a_sbo);
+                  for (int ks = 0; ks < nks; ++ks)      // the very first K step of a sub-tile overwrites, all others accumulate
+                    umma_f16(d_tmem + u * p.NT, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)(ks > 0));
+                }
+                if (kCluster) umma_commit_mc(bempty0 + 8 * ib, (uint16_t)3); else umma_commit(bempty0 + 8 * ib);
+                if (r == 2) umma_commit(aempty0 + 8 * ia);
               }
+              __syncwarp();
               accumulate = 1;
-              if (kCluster) umma_commit_mc(bempty0 + 8 * ib, (uint16_t)3); else umma_commit(bempty0 + 8 * ib);
               if (++ib == p.rb) { ib = 0; pb ^= 1; }
             }
-            umma_commit(aempty0 + 8 * ia);
             if (++ia == p.ra) { ia = 0; pa ^= 1; }
           }
         }
       }
-      umma_commit(tfull0 + 8 * as);
+      if (elect_one()) umma_commit(tfull0 + 8 * as);
+      __syncwarp();
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int quarter = warp & 3;
+    // ===================== epilogue (4 warps) =====================
+    const int ew = warp - 4, quarter = warp & 3;
     const int row = quarter * 32 + lane;             // MMA row = dy*8 + dx of the sub-tile
     uint32_t acc_phase0 = 0, acc_phase1 = 0;
-    int it = 0;
-    const int nchunks = p.NT >> 4;
+    int it = 0, bias_combo = -1;
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
     for (long long unit = unit0; unit < n_units; unit += unit_step, ++it) {
       const int as = it & 1;
       const int combo = (int)(unit % ncombo);
@@ -501,20 +589,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
       const int hh = (rem / p.tiles_w) * 16 + (row >> 3);
       const uint32_t aph = as ? acc_phase1 : acc_phase0;
-      mbar_wait(tfull0 + 8 * as, aph);
       if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
-      tc_fence_after();
       for (int u = 0; u < p.nsub; ++u) {
         const int ww = (rem % p.tiles_w) * tw_cols + 8 * u + (row & 7);
         const bool pvalid = hh < p.H && ww < p.W && img < p.n_img;
-        const long long pix = ((long long)img * p.H + hh) * p.W + ww;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_STRIDE + u * p.NT;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          uint32_t raw[16];
-          __syncwarp();
-          tmem_ld16(taddr + ch * 16, raw);
-          epilogue_chunk(p, raw, pvalid, img, hh, ww, pix, g, nt, ch);
-        }
+        epilogue_tile<4>(p, bias_s, bias_combo, combo, ew, lane, taddr, img, hh, ww, pvalid, g, nt, tfull0 + 8 * as, aph, u == 0);
       }
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * as);
@@ -604,13 +684,13 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   p.out_dt = out_dt; p.out_pitch = out_pitch; p.res_dt = res_dt; p.res_pitch = res_pitch; p.aux_dt = aux_dt; p.aux_pitch = aux_pitch;
   p.act = act; p.alpha = act_alpha; p.out_scale = out_scale; p.epi = epi; p.res_scale = res_scale; p.ps = pixel_shuffle;
   p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0;
-  const int budget = g_smem_optin - 1024 - 512;
+  const int budget = g_smem_optin - 1024 - 512 - 1024;     // alignment slack, barriers, bias staging
 
   // variant: 0 = auto, 1 = force the per-tap kernel, 2 = 3x3 kernel with nsub = 1, 3 = 3x3 kernel with nsub = 2;
   // +4 = 2-CTA cluster with multicast weight boxes (3x3 kernel only)
   const bool cluster = (variant & 4) != 0;
   variant &= 3;
-  const bool use3x3 = R == 3 && S == 3 && H >= 8 && W >= 8 && variant != 1;
+  const bool use3x3 = R == 3 && S == 3 && H >= 8 && W >= 8 && variant >= 2;     // explicit request only (see ops.py)
   if (cluster && !use3x3) return VMGB_EINVAL;
   if (use3x3) {
     p.nsub = (variant == 2) ? 1 : ((2 * p.NT <= ACC_STRIDE && W > 8) ? 2 : 1);
@@ -656,7 +736,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   }
   const long long grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   if (use3x3 && cluster) {
-    const int smem = p.ra * p.a_unit_bytes + p.rb * p.b_stage_bytes + 1024 + 512;
+    const int smem = p.ra * p.a_unit_bytes + p.rb * p.b_stage_bytes + 1024 + 512 + 1024;
     const long long n_mt = (long long)n_img * p.tiles_h * p.tiles_w;
     const long long units = ((n_mt + 1) / 2) * groups * p.nt_per_g;
     long long clusters = units < g_num_sms / 2 ? units : g_num_sms / 2;
@@ -668,11 +748,11 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<true>, mA[0], mA[1], mA[2], mB, p);
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return VMGB_ECUDA; }
   } else if (use3x3) {
-    const int smem = p.ra * p.a_unit_bytes + p.rb * p.b_stage_bytes + 1024 + 512;
+    const int smem = p.ra * p.a_unit_bytes + p.rb * p.b_stage_bytes + 1024 + 512 + 1024;
     conv3x3_tc_kernel<false><<<(unsigned)grid, 256, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
   } else {
-    const int smem = p.stages * (A_STAGE_BYTES + p.b_stage_bytes) + 1024 + 512;
-    conv_tc_kernel<<<(unsigned)grid, 256, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
+    const int smem = p.stages * (A_STAGE_BYTES + p.b_stage_bytes) + 1024 + 512 + 1024;
+    conv_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
   }
   return check_launch();
 }

@@ -450,8 +450,8 @@ class VMG(nn.Module):
             if is_key:
                 K += 1                                  # step j becomes key frame K-1 once fbuf[j] is written
             prev = self._resblocks(tm.resblocks, (xp[j], feat_in), fbuf[j])
-        back = fbuf[:, :n].flip(0).reshape(N, H, W, C)  # outputs_back[i] = backward sweep at step T-1-i
-        fwd = fbuf[:, n:].reshape(N, H, W, C)
+        back = fbuf[:, :n].flip(0).contiguous().view(N, H, W, C)  # outputs_back[i] = backward sweep at step T-1-i
+        fwd = fbuf[:, n:].contiguous().view(N, H, W, C)
         return o.conv2d((back, x, fwd), self._pc(tm.fusion), act=o.ACT_LRELU, alpha=0.1)
 
     # -------------------------------------------------------------------------------------------
