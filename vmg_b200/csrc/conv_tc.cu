@@ -29,6 +29,7 @@ struct TcP {
   int act; float alpha, out_scale; int epi; float res_scale; int ps;
   int b_stage_bytes;
   int nsub, ra, rb, a_unit_bytes, a_sbo;       // 3x3 kernel (conv3x3_tc_kernel) only
+  int res_smem;                                // per-tap kernel: bytes of ONE residual staging buffer (0 = off)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -401,10 +402,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
-    const int ew = warp - 4, quarter = warp & 3;
+    // Residual rows are staged global -> shared with cp.async ONE TILE AHEAD (double buffer), so the L2 round
+    // trip of the residual read rides under the previous tile's drain instead of stalling this one.
+    // Staging layout: [chunk][128 rows][16 bf16] -- every thread writes and reads only its own 32-byte cells.
+    const int ew = warp - 4, quarter = warp & 3, half = ew >> 2;
     const int row = quarter * 32 + lane;
+    const int nchunks = p.NT >> 4;
     uint32_t acc_phase0 = 0, acc_phase1 = 0;
     int it = 0, bias_combo = -1;
+    const bool stage_res = p.res_smem > 0 && p.epi != VMGB_EPI_STORE;
+    const uint32_t res_s0 = smem_u32(bias_s) + 1024;          // two buffers of p.res_smem bytes after the bias
+    auto issue_residual = [&](long long tile, int buf) {
+      if (tile < p.total_tiles) {
+        const int combo = (int)(tile % ncombo); const long long mt = tile / ncombo;
+        const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+        const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
+        const int hh = (rem / p.tiles_w) * p.BH + row / p.BW, ww = (rem % p.tiles_w) * p.BW + row % p.BW;
+        const bool pvalid = hh < p.H && ww < p.W;
+        const long long pix = ((long long)img * p.H + hh) * p.W + ww;
+        for (int ch = half; ch < nchunks; ch += 2) {
+          if (pre_ok(p, pvalid, g, nt * p.NT + ch * 16)) {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_pitch + g * p.Cout_g + nt * p.NT + ch * 16;
+            const uint32_t dst = res_s0 + buf * p.res_smem + (ch * 128 + row) * 32;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rp) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(rp + 8) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (stage_res) issue_residual(blockIdx.x, 0);
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const int combo = (int)(tile % ncombo); const long long mt = tile / ncombo;
@@ -412,13 +439,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
       const int hh = (rem / p.tiles_w) * p.BH + row / p.BW, ww = (rem % p.tiles_w) * p.BW + row % p.BW;
       const bool pvalid = hh < p.H && ww < p.W;
+      const long long pix = ((long long)img * p.H + hh) * p.W + ww;
       const uint32_t aph = as ? acc_phase1 : acc_phase0;
       if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_STRIDE;
-      epilogue_tile<8>(p, bias_s, bias_combo, combo, ew, lane, taddr, img, hh, ww, pvalid, g, nt, tfull0 + 8 * as, aph, true);
+      if (stage_res) {
+        issue_residual(tile + gridDim.x, (it + 1) & 1);                     // next tile's residual, one tile ahead
+        asm volatile("cp.async.wait_group 1;" ::: "memory");               // this tile's residual has landed
+      }
+      if (combo != bias_combo) {                                            // bias of this (group, N tile) -> smem
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int c = ew * 32 + lane; c < p.NT; c += 256) {
+          const int nb = nt * p.NT + c;
+          bias_s[c] = (p.bias && nb < p.Cout_g) ? __ldg(p.bias + g * p.Cout_g + nb) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        bias_combo = combo;
+      }
+      mbar_wait(tfull0 + 8 * as, aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = half; ch < nchunks; ch += 2) {
+        uint32_t raw[16];
+        __syncwarp();
+        tmem_ld16(taddr + ch * 16, raw);
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+        const bool hp = stage_res && pre_ok(p, pvalid, g, nt * p.NT + ch * 16);
+        if (hp) {
+          const uint32_t src = res_s0 + (it & 1) * p.res_smem + (ch * 128 + row) * 32;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(src));
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(src + 16));
+        }
+        epilogue_chunk(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, r0, r1);
+      }
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * as);
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
 
   tc_fence_before();
@@ -683,7 +740,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   p.bias = (const float*)bias; p.out = out; p.res = res; p.aux = aux;
   p.out_dt = out_dt; p.out_pitch = out_pitch; p.res_dt = res_dt; p.res_pitch = res_pitch; p.aux_dt = aux_dt; p.aux_pitch = aux_pitch;
   p.act = act; p.alpha = act_alpha; p.out_scale = out_scale; p.epi = epi; p.res_scale = res_scale; p.ps = pixel_shuffle;
-  p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0;
+  p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0; p.res_smem = 0;
   const int budget = g_smem_optin - 1024 - 512 - 1024;     // alignment slack, barriers, bias staging
 
   // variant: 0 = auto, 1 = force the per-tap kernel, 2 = 3x3 kernel with nsub = 1, 3 = 3x3 kernel with nsub = 2;
@@ -708,7 +765,11 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
     if (H == 1) { p.BW = 128; p.BH = 1; }
     else { p.BW = W >= 16 ? 16 : (W >= 8 ? 8 : 4); p.BH = 128 / p.BW; }
     const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
-    p.stages = budget / stage_bytes;
+    // residual staging (2 buffers of 128 rows x NT bf16) when it leaves at least 4 pipeline stages
+    p.res_smem = 0;
+    if (epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0 && (budget - 2 * p.NT * 256) / stage_bytes >= 4)
+      p.res_smem = p.NT * 256;
+    p.stages = (budget - 2 * p.res_smem) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return VMGB_EUNSUPPORTED;
   }
@@ -751,7 +812,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
     const int smem = p.ra * p.a_unit_bytes + p.rb * p.b_stage_bytes + 1024 + 512 + 1024;
     conv3x3_tc_kernel<false><<<(unsigned)grid, 256, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
   } else {
-    const int smem = p.stages * (A_STAGE_BYTES + p.b_stage_bytes) + 1024 + 512 + 1024;
+    const int smem = p.stages * (A_STAGE_BYTES + p.b_stage_bytes) + 1024 + 512 + 1024 + 2 * p.res_smem;
     conv_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
   }
   return check_launch();
