@@ -100,7 +100,7 @@ C3 = [
 ]
 
 
-@pytest.mark.parametrize('variant', [0, 1, 2, 3, 6, 7], ids=['auto', 'per_tap', '3x3_nsub1', '3x3_nsub2', '3x3_nsub1_cluster2', '3x3_nsub2_cluster2'])
+@pytest.mark.parametrize('variant', [0, 1, 2, 3, 6, 7, 8], ids=['auto', 'per_tap', '3x3_nsub1', '3x3_nsub2', '3x3_nsub1_cluster2', '3x3_nsub2_cluster2', 'weight_stationary'])
 @pytest.mark.parametrize('case', C3, ids=lambda c: 'x'.join(map(str, c)))
 def test_conv3x3_variants(case, variant):
     N, H, W, Cin, Cout, R, groups, act, epi, ps, n_src = case
@@ -109,7 +109,12 @@ def test_conv3x3_variants(case, variant):
     NT = -(-(-(-cg // nt)) // 16) * 16
     if (variant & 3) == 3 and 2 * NT > 256:
         pytest.skip('two sub-tiles need 2*NT <= 256 TMEM columns per accumulator set')
-    out, ref = conv_case(N, H, W, Cin, Cout, R, groups, torch.bfloat16, True, n_src, act, epi, ps, out_dtype=torch.float32, variant=variant)
+    try:
+        out, ref = conv_case(N, H, W, Cin, Cout, R, groups, torch.bfloat16, True, n_src, act, epi, ps, out_dtype=torch.float32, variant=variant)
+    except RuntimeError as e:
+        if variant == 8 and 'code -2' in str(e):
+            pytest.skip('weights of one output slice do not fit in shared memory (VMGB_EUNSUPPORTED)')
+        raise
     close(out, ref, 2e-3)
 
 

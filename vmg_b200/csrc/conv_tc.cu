@@ -299,6 +299,115 @@ __device__ __forceinline__ void epilogue_tile(const TcP& p, float* bias_s, int& 
 }
 
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Epilogue driver of the 384-thread kernels (8 epilogue warps).  `decode(t, row, combo, img, hh, ww, pvalid)`
+// maps work item t and accumulator row to the output pixel.  Residual rows are staged global -> shared with
+// cp.async ONE ITEM AHEAD (double buffer [chunk][128 rows][16 bf16], each thread touches only its own cells),
+// so the L2 round trip of the residual read rides under the previous drain instead of stalling this one.
+// ---------------------------------------------------------------------------------------------
+template <class Decode>
+__device__ __forceinline__ void run_epilogue(const TcP& p, float* bias_s, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                             long long first, long long step, long long total, int warp, int lane, Decode decode) {
+  const int ew = warp - 4, quarter = warp & 3, half = ew >> 2;
+  const int row = quarter * 32 + lane;
+  const int nchunks = p.NT >> 4;
+  uint32_t acc_phase0 = 0, acc_phase1 = 0;
+  int it = 0, bias_combo = -1;
+  const bool stage_res = p.res_smem > 0 && p.epi != VMGB_EPI_STORE;
+  // without smem staging (weight-stationary kernel short of shared memory): same one-item-ahead idea in registers,
+  // for up to 2 chunks per thread (NT <= 64)
+  const bool reg_res = !stage_res && p.epi != VMGB_EPI_STORE && p.res_dt == VMGB_BF16 && p.ps == 0 && nchunks <= 4;
+  uint4 cur[2][2], nxt[2][2];
+  auto load_regs = [&](long long t, uint4 (&dst)[2][2]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { dst[i][0] = make_uint4(0, 0, 0, 0); dst[i][1] = dst[i][0]; }
+    if (t < total) {
+      int combo, img, hh, ww; bool pvalid;
+      decode(t, row, combo, img, hh, ww, pvalid);
+      const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+      const long long pix = ((long long)img * p.H + hh) * p.W + ww;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int ch = half + 2 * i;
+        if (ch < nchunks && pre_ok(p, pvalid, g, nt * p.NT + ch * 16)) {
+          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_pitch + g * p.Cout_g + nt * p.NT + ch * 16;
+          dst[i][0] = ldg_nc_v4(rp); dst[i][1] = ldg_nc_v4(rp + 8);
+        }
+      }
+    }
+  };
+  if (reg_res) load_regs(first, cur);
+  const uint32_t res_s0 = smem_u32(bias_s) + 1024;          // two buffers of p.res_smem bytes after the bias
+  auto issue_residual = [&](long long t, int buf) {
+    if (t < total) {
+      int combo, img, hh, ww; bool pvalid;
+      decode(t, row, combo, img, hh, ww, pvalid);
+      const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+      const long long pix = ((long long)img * p.H + hh) * p.W + ww;
+      for (int ch = half; ch < nchunks; ch += 2) {
+        if (pre_ok(p, pvalid, g, nt * p.NT + ch * 16)) {
+          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_pitch + g * p.Cout_g + nt * p.NT + ch * 16;
+          const uint32_t dst = res_s0 + buf * p.res_smem + (ch * 128 + row) * 32;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rp) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(rp + 8) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (stage_res) issue_residual(first, 0);
+  for (long long t = first; t < total; t += step, ++it) {
+    const int as = it & 1;
+    int combo, img, hh, ww; bool pvalid;
+    decode(t, row, combo, img, hh, ww, pvalid);
+    const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+    const long long pix = ((long long)img * p.H + hh) * p.W + ww;
+    const uint32_t aph = as ? acc_phase1 : acc_phase0;
+    if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_STRIDE;
+    if (stage_res) {
+      issue_residual(t + step, (it + 1) & 1);                             // next item's residual, one item ahead
+      asm volatile("cp.async.wait_group 1;" ::: "memory");               // this item's residual has landed
+    }
+    if (reg_res) load_regs(t + step, nxt);
+    if (combo != bias_combo) {                                            // bias of this (group, N tile) -> smem
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int c = ew * 32 + lane; c < p.NT; c += 256) {
+        const int nb = nt * p.NT + c;
+        bias_s[c] = (p.bias && nb < p.Cout_g) ? __ldg(p.bias + g * p.Cout_g + nb) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      bias_combo = combo;
+    }
+    mbar_wait(tfull0 + 8 * as, aph);
+    tc_fence_after();
+#pragma unroll 1
+    for (int ch = half; ch < nchunks; ch += 2) {
+      uint32_t raw[16];
+      __syncwarp();
+      tmem_ld16(taddr + ch * 16, raw);
+      uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+      const bool hp = (stage_res || reg_res) && pre_ok(p, pvalid, g, nt * p.NT + ch * 16);
+      if (hp && stage_res) {
+        const uint32_t src = res_s0 + (it & 1) * p.res_smem + (ch * 128 + row) * 32;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(src));
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(src + 16));
+      } else if (hp) {
+        const bool second = ch >= half + 2;
+        r0 = second ? cur[1][0] : cur[0][0]; r1 = second ? cur[1][1] : cur[0][1];
+      }
+      epilogue_chunk(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, r0, r1);
+    }
+    tc_fence_before();
+    mbar_arrive(tempty0 + 8 * as);
+    if (reg_res) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { cur[i][0] = nxt[i][0]; cur[i][1] = nxt[i][1]; }
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 constexpr int TC_THREADS = 384;      // warps 0-3: producer / MMA / TMEM alloc / spare ; warps 4-11: epilogue
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -402,80 +511,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
-    // Residual rows are staged global -> shared with cp.async ONE TILE AHEAD (double buffer), so the L2 round
-    // trip of the residual read rides under the previous tile's drain instead of stalling this one.
-    // Staging layout: [chunk][128 rows][16 bf16] -- every thread writes and reads only its own 32-byte cells.
-    const int ew = warp - 4, quarter = warp & 3, half = ew >> 2;
-    const int row = quarter * 32 + lane;
-    const int nchunks = p.NT >> 4;
-    uint32_t acc_phase0 = 0, acc_phase1 = 0;
-    int it = 0, bias_combo = -1;
-    const bool stage_res = p.res_smem > 0 && p.epi != VMGB_EPI_STORE;
-    const uint32_t res_s0 = smem_u32(bias_s) + 1024;          // two buffers of p.res_smem bytes after the bias
-    auto issue_residual = [&](long long tile, int buf) {
-      if (tile < p.total_tiles) {
-        const int combo = (int)(tile % ncombo); const long long mt = tile / ncombo;
-        const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
-        const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
-        const int hh = (rem / p.tiles_w) * p.BH + row / p.BW, ww = (rem % p.tiles_w) * p.BW + row % p.BW;
-        const bool pvalid = hh < p.H && ww < p.W;
-        const long long pix = ((long long)img * p.H + hh) * p.W + ww;
-        for (int ch = half; ch < nchunks; ch += 2) {
-          if (pre_ok(p, pvalid, g, nt * p.NT + ch * 16)) {
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_pitch + g * p.Cout_g + nt * p.NT + ch * 16;
-            const uint32_t dst = res_s0 + buf * p.res_smem + (ch * 128 + row) * 32;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rp) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(rp + 8) : "memory");
-          }
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    if (stage_res) issue_residual(blockIdx.x, 0);
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const int combo = (int)(tile % ncombo); const long long mt = tile / ncombo;
-      const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
-      const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
-      const int hh = (rem / p.tiles_w) * p.BH + row / p.BW, ww = (rem % p.tiles_w) * p.BW + row % p.BW;
-      const bool pvalid = hh < p.H && ww < p.W;
-      const long long pix = ((long long)img * p.H + hh) * p.W + ww;
-      const uint32_t aph = as ? acc_phase1 : acc_phase0;
-      if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_STRIDE;
-      if (stage_res) {
-        issue_residual(tile + gridDim.x, (it + 1) & 1);                     // next tile's residual, one tile ahead
-        asm volatile("cp.async.wait_group 1;" ::: "memory");               // this tile's residual has landed
-      }
-      if (combo != bias_combo) {                                            // bias of this (group, N tile) -> smem
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int c = ew * 32 + lane; c < p.NT; c += 256) {
-          const int nb = nt * p.NT + c;
-          bias_s[c] = (p.bias && nb < p.Cout_g) ? __ldg(p.bias + g * p.Cout_g + nb) : 0.f;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        bias_combo = combo;
-      }
-      mbar_wait(tfull0 + 8 * as, aph);
-      tc_fence_after();
-#pragma unroll 1
-      for (int ch = half; ch < nchunks; ch += 2) {
-        uint32_t raw[16];
-        __syncwarp();
-        tmem_ld16(taddr + ch * 16, raw);
-        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
-        const bool hp = stage_res && pre_ok(p, pvalid, g, nt * p.NT + ch * 16);
-        if (hp) {
-          const uint32_t src = res_s0 + (it & 1) * p.res_smem + (ch * 128 + row) * 32;
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(src));
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(src + 16));
-        }
-        epilogue_chunk(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, r0, r1);
-      }
-      tc_fence_before();
-      mbar_arrive(tempty0 + 8 * as);
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    run_epilogue(p, bias_s, tmem_base, tfull0, tempty0, (long long)blockIdx.x, (long long)gridDim.x, p.total_tiles, warp, lane,
+                 [&](long long tile, int row, int& combo, int& img, int& hh, int& ww, bool& pvalid) {
+                   combo = (int)(tile % ncombo);
+                   const long long mt = tile / ncombo;
+                   img = (int)(mt / tiles_per_img);
+                   const int rem = (int)(mt % tiles_per_img);
+                   hh = (rem / p.tiles_w) * p.BH + row / p.BW;
+                   ww = (rem % p.tiles_w) * p.BW + row % p.BW;
+                   pvalid = hh < p.H && ww < p.W;
+                 });
   }
 
   tc_fence_before();
@@ -667,6 +712,155 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 convolution, WEIGHT-STATIONARY variant (the trajectory resblock convs: 63-67 % of all FLOPs).
+// Measured on B200: the per-tap kernel is bound by the L2 -> SM fabric (~9 TB/s aggregate, ~60 GB/s per SM),
+// moving 484 KB per 128-pixel tile at C = N = 112, of which 226 KB are the same weights again and again.
+// Here the output channels of a group are split into `nt_per_g` slices of NT columns and every CTA keeps the
+// COMPLETE weight set of one slice (9 taps x K blocks, <= ~150 KB) resident in shared memory for the whole
+// launch; only activations stream, as column-shifted 18-row "A units" (see conv3x3_tc_kernel): one TMA box
+// {64 ch, 8 cols, 18 rows} per (K block, column shift) serves the three taps of that shift.  Per tile and
+// slice the fabric moves ~97 KB instead of 484 KB.
+// Work split: CTA b owns combo = b % (groups*slices) for the whole launch and walks the M tiles
+// b / ncombo, b / ncombo + grid / ncombo, ...
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv3x3_ws_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB, const TcP p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nboxes = p.n_src * p.kb_per_src * 9;
+  const uint32_t a_base = smem_base;
+  const uint32_t w_base = a_base + p.ra * p.a_unit_bytes;
+  const uint32_t bar_base = w_base + nboxes * p.b_stage_bytes;
+  const uint32_t afull0 = bar_base, aempty0 = afull0 + 8 * p.ra;
+  const uint32_t wfull = aempty0 + 8 * p.ra;
+  const uint32_t tfull0 = wfull + 16, tempty0 = tfull0 + 16;      // keeps the bias staging 16-byte aligned
+  const uint32_t tmem_slot = tempty0 + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.ra; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
+    mbar_init(wfull, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
+
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int ncombo = p.groups * p.nt_per_g;
+  const int combo = (int)(blockIdx.x % ncombo);
+  const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+  const long long first = blockIdx.x / ncombo, step = gridDim.x / ncombo;
+  const long long n_mt = (long long)p.n_img * tiles_per_img;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {                 // the whole weight slice, once
+      mbar_expect_tx(wfull, (uint32_t)(nboxes * p.NT * 128));
+      for (int src = 0; src < p.n_src; ++src)
+        for (int kb = 0; kb < p.kb_per_src; ++kb)
+          for (int tap = 0; tap < 9; ++tap)
+            tma_load_2d(w_base + ((src * p.kb_per_src + kb) * 9 + tap) * p.b_stage_bytes, &mapB, wfull, src * p.Cs + kb * 64,
+                        (g * 9 + tap) * p.Cout_g + nt * p.NT);
+    }
+    __syncwarp();
+    int ia = 0; uint32_t pa = 0;
+    const uint32_t a_bytes = 18 * 8 * 128;
+    for (long long mt = first; mt < n_mt; mt += step) {
+      const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
+      const int h0 = (rem / p.tiles_w) * 16, w0 = (rem % p.tiles_w) * 8;
+      for (int src = 0; src < p.n_src; ++src) {
+        const CUtensorMap* mA = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
+        for (int kb = 0; kb < p.kb_per_src; ++kb) {
+          const int ca = (p.n_src > 1 ? 0 : ((g * p.Cin_g) & ~7)) + kb * 64;
+          for (int sft = 0; sft < 3; ++sft) {
+            mbar_wait(aempty0 + 8 * ia, pa ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(afull0 + 8 * ia, a_bytes);
+              tma_load_4d(a_base + ia * p.a_unit_bytes, mA, afull0 + 8 * ia, ca, w0 + sft - 1, h0 - 1, img);
+            }
+            __syncwarp();
+            if (++ia == p.ra) { ia = 0; pa ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const int kext = p.Cs + (p.n_src > 1 ? 0 : ((g * p.Cin_g) & 7));
+    int ia = 0; uint32_t pa = 0;
+    uint32_t acc_phase0 = 0, acc_phase1 = 0;
+    int it = 0;
+    mbar_wait(wfull, 0);
+    tc_fence_after();
+    for (long long mt = first; mt < n_mt; mt += step, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = as ? acc_phase1 : acc_phase0;
+      mbar_wait(tempty0 + 8 * as, aph ^ 1);
+      if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+      uint32_t accumulate = 0;
+      for (int src = 0; src < p.n_src; ++src) {
+        for (int kb = 0; kb < p.kb_per_src; ++kb) {
+          const int nks = min(4, (kext - kb * 64 + 15) >> 4);
+          const bool last_kb = src == p.n_src - 1 && kb == p.kb_per_src - 1;
+          for (int sft = 0; sft < 3; ++sft) {
+            mbar_wait(afull0 + 8 * ia, pa);
+            tc_fence_after();
+            const uint32_t a_unit = a_base + ia * p.a_unit_bytes;
+            if (elect_one()) {
+              for (int r = 0; r < 3; ++r) {
+                const uint64_t ad = smem_desc_sw128(a_unit + (uint32_t)r * 1024u);
+                const uint64_t bd = smem_desc_sw128(w_base + ((src * p.kb_per_src + kb) * 9 + r * 3 + sft) * p.b_stage_bytes);
+                for (int ks = 0; ks < nks; ++ks)
+                  umma_f16(d_tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)((r | ks) > 0));
+              }
+              umma_commit(aempty0 + 8 * ia);
+              if (last_kb && sft == 2) umma_commit(tfull0 + 8 * as);
+            }
+            __syncwarp();
+            accumulate = 1;
+            if (++ia == p.ra) { ia = 0; pa ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps) =====================
+    run_epilogue(p, bias_s, tmem_base, tfull0, tempty0, first, step, n_mt, warp, lane,
+                 [&](long long mt, int row, int& cmb, int& img, int& hh, int& ww, bool& pvalid) {
+                   cmb = combo;
+                   img = (int)(mt / tiles_per_img);
+                   const int rem = (int)(mt % tiles_per_img);
+                   hh = (rem / p.tiles_w) * 16 + (row >> 3);
+                   ww = (rem % p.tiles_w) * 8 + (row & 7);
+                   pvalid = hh < p.H && ww < p.W;
+                 });
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -691,6 +885,7 @@ static void tc_init() {
     cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
     cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
     cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+    cudaFuncSetAttribute(conv3x3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
   }
 }
 
@@ -742,6 +937,54 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   p.act = act; p.alpha = act_alpha; p.out_scale = out_scale; p.epi = epi; p.res_scale = res_scale; p.ps = pixel_shuffle;
   p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0; p.res_smem = 0;
   const int budget = g_smem_optin - 1024 - 512 - 1024;     // alignment slack, barriers, bias staging
+
+  // ---- weight-stationary 3x3 kernel (variant 8, or auto when the launch is large enough to amortise the
+  //      one-off weight load): find the smallest number of output-channel slices whose weights fit
+  if (R == 3 && S == 3 && H >= 8 && W >= 8 && (variant == 8 || variant == 0)) {
+    const int nboxes = n_src * p.kb_per_src * 9;
+    const long long n_mt = (long long)n_img * ((H + 15) / 16) * ((W + 7) / 8);
+    int best_slices = 0, best_nt = 0, best_ra = 0, best_res = 0;
+    for (int sl = 1; sl <= 8 && !best_slices; ++sl) {
+      const int nts = (((Cout_g + sl - 1) / sl) + 15) / 16 * 16;
+      if (nts > 256) continue;
+      int resb = (epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0) ? nts * 256 : 0;
+      int ra = (budget - nboxes * nts * 128 - 2 * resb) / (18 * 8 * 128);
+      if (ra >= 2) { best_slices = sl; best_nt = nts; best_ra = ra > 6 ? 6 : ra; best_res = resb; }
+    }
+    const long long ctas = g_num_sms / (groups * (best_slices ? best_slices : 1));
+    // auto: measured wins (tools/microbench.py) are the single-source, ungrouped convs with <= 2 K blocks
+    // (trajectory resblocks at C=112, recon head); at least ~4 M tiles per CTA amortise the resident weight load
+    const bool worth = best_slices && ctas >= 1 && n_mt >= 4 * ctas && n_src == 1 && groups == 1 && p.kb_per_src <= 2;
+    if (best_slices && ctas >= 1 && (variant == 8 || worth)) {
+      p.nt_per_g = best_slices; p.NT = best_nt; p.b_stage_bytes = best_nt * 128; p.ra = best_ra; p.res_smem = best_res;
+      p.BH = 16; p.BW = 8; p.a_unit_bytes = 18 * 8 * 128; p.stages = 0;
+      p.tiles_h = (H + 15) / 16; p.tiles_w = (W + 7) / 8;
+      p.total_tiles = n_mt * groups * p.nt_per_g;
+      CUtensorMap mA[3], mB;
+      const void* srcs[3] = {x, x1, x2};
+      const int c_extent = n_src > 1 ? p.Cs : Cin;
+      for (int s = 0; s < 3; ++s) {
+        const void* ptr = s < n_src ? srcs[s] : x;
+        if (reinterpret_cast<uintptr_t>(ptr) & 15) return VMGB_EINVAL;
+        cuuint64_t dims[4] = {(cuuint64_t)c_extent, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+        cuuint64_t str[3] = {(cuuint64_t)x_pitch * 2, (cuuint64_t)W * x_pitch * 2, (cuuint64_t)H * W * x_pitch * 2};
+        cuuint32_t box[4] = {64, 8, 18, 1};
+        if (!encode_bf16(&mA[s], ptr, 4, dims, str, box)) return VMGB_EINVAL;
+      }
+      {
+        cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)groups * 9 * Cout_g};
+        cuuint64_t str[1] = {(cuuint64_t)Kp * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)p.NT};
+        if (!encode_bf16(&mB, w, 2, dims, str, box)) return VMGB_EINVAL;
+      }
+      const int ncombo = groups * p.nt_per_g;
+      long long per = n_mt < ctas ? n_mt : ctas;
+      const int smem = p.ra * p.a_unit_bytes + nboxes * p.b_stage_bytes + 1024 + 512 + 1024 + 2 * p.res_smem;
+      conv3x3_ws_kernel<<<(unsigned)(per * ncombo), TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
+      return check_launch();
+    }
+    if (variant == 8) return VMGB_EUNSUPPORTED;
+  }
 
   // variant: 0 = auto, 1 = force the per-tap kernel, 2 = 3x3 kernel with nsub = 1, 3 = 3x3 kernel with nsub = 2;
   // +4 = 2-CTA cluster with multicast weight boxes (3x3 kernel only)
