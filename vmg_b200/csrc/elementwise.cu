@@ -88,6 +88,36 @@ __global__ void __launch_bounds__(256) l2norm_vec_kernel(const void* x, int x_dt
   }
 }
 
+// narrow rows (C <= 128, C % 4 == 0): one vector per lane, ROWS independent rows per warp iteration so that
+// several 8..16-byte loads per lane are in flight (a single 224-byte row per warp leaves HBM latency exposed)
+template <int ROWS>
+__global__ void __launch_bounds__(256) layernorm_narrow_kernel(const void* x, int x_dt, void* out, int out_dt,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int c = 4 * lane;
+  const bool act = c < C;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f), b = g;
+  if (act) { g = *reinterpret_cast<const float4*>(gamma + c); b = *reinterpret_cast<const float4*>(beta + c); }
+  for (long long r0 = warp_id * ROWS; r0 < rows; r0 += nwarps * ROWS) {
+    float4 v[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k)
+      v[k] = (act && r0 + k < rows) ? ld4(x, x_dt, (r0 + k) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+      const float mean = warp_sum((v[k].x + v[k].y) + (v[k].z + v[k].w)) / (float)C;
+      const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;
+      const float q = act ? (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3) : 0.f;
+      const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+      if (act && r0 + k < rows)
+        st4(out, out_dt, (r0 + k) * C + c, make_float4(d0 * rstd * g.x + b.x, d1 * rstd * g.y + b.y, d2 * rstd * g.z + b.z, d3 * rstd * g.w + b.w));
+    }
+  }
+}
+
 // L2 normalise (F.normalize, eps 1e-12)
 __global__ void __launch_bounds__(256) l2norm_kernel(const void* x, int x_dt, int x_pitch, void* out, int out_dt,
                                                      long long rows, int C) {
@@ -151,6 +181,7 @@ __global__ void morph_scatter_kernel(const void* Y, int y_dt, void* out, int out
 // C-element pixel rows, in-smem (r, g, s) -> (g, r, s) transpose, coalesced writes.  inverse = scatter.
 // ---------------------------------------------------------------------------------------------
 constexpr int MORPH_WARPS = 4;
+template <bool VEC>
 __global__ void __launch_bounds__(32 * MORPH_WARPS) morph_block_kernel(const void* src, int src_dt, void* dst, int dst_dt, int BT, int H,
                                                                       int W, int C, int ch, int axis, int inverse, long long n_blocks) {
   extern __shared__ float sm_all[];
@@ -163,30 +194,54 @@ __global__ void __launch_bounds__(32 * MORPH_WARPS) morph_block_kernel(const voi
   // block index = (bt*O + o)*Lg + lg  (same order as the row index / ch)
   const int lg = (int)(blk % Lg); const long long t = blk / Lg; const int o = (int)(t % O); const int bt = (int)(t / O);
   const long long rows0 = blk * ch;                     // first A row of this block
+  constexpr int V = VEC ? 4 : 1;
+  const int Cv = C / V, Cpv = Cp / V;
   if (!inverse) {
     for (int i = lane; i < ch * Cp; i += 32) sm[i] = 0.f;
     __syncwarp();
-    for (int i = lane; i < ch * C; i += 32) {
-      const int r = i / C, c = i - r * C;
+    for (int i = lane; i < ch * Cv; i += 32) {
+      const int r = i / Cv, c = (i - r * Cv) * V;
       const int l = lg * ch + r;
       if (l < L) {
         const int h = axis == 0 ? l : o, w = axis == 0 ? o : l;
-        const int g = c / S, s2 = c - g * S;
-        sm[g * Cp + r * S + s2] = ldf(src, src_dt, (((long long)bt * H + h) * W + w) * C + c);
+        const long long gi = (((long long)bt * H + h) * W + w) * C + c;
+        if (VEC) {
+          const float4 v = ld4(src, src_dt, gi);
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const int g = (c + k) / S, s2 = (c + k) - g * S; sm[g * Cp + r * S + s2] = vv[k]; }
+        } else {
+          const int g = c / S, s2 = c - g * S;
+          sm[g * Cp + r * S + s2] = ldf(src, src_dt, gi);
+        }
       }
     }
     __syncwarp();
-    for (int i = lane; i < ch * Cp; i += 32) stf(dst, dst_dt, rows0 * Cp + i, sm[i]);
+    for (int i = lane; i < ch * Cpv; i += 32) {
+      if (VEC) st4(dst, dst_dt, rows0 * Cp + 4 * i, *reinterpret_cast<const float4*>(sm + 4 * i));
+      else stf(dst, dst_dt, rows0 * Cp + i, sm[i]);
+    }
   } else {
-    for (int i = lane; i < ch * Cp; i += 32) sm[i] = ldf(src, src_dt, rows0 * Cp + i);
+    for (int i = lane; i < ch * Cpv; i += 32) {
+      if (VEC) *reinterpret_cast<float4*>(sm + 4 * i) = ld4(src, src_dt, rows0 * Cp + 4 * i);
+      else sm[i] = ldf(src, src_dt, rows0 * Cp + i);
+    }
     __syncwarp();
-    for (int i = lane; i < ch * C; i += 32) {
-      const int r = i / C, c = i - r * C;
+    for (int i = lane; i < ch * Cv; i += 32) {
+      const int r = i / Cv, c = (i - r * Cv) * V;
       const int l = lg * ch + r;
       if (l < L) {
         const int h = axis == 0 ? l : o, w = axis == 0 ? o : l;
-        const int g = c / S, s2 = c - g * S;
-        stf(dst, dst_dt, (((long long)bt * H + h) * W + w) * C + c, sm[g * Cp + r * S + s2]);
+        const long long gi = (((long long)bt * H + h) * W + w) * C + c;
+        if (VEC) {
+          float vv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const int g = (c + k) / S, s2 = (c + k) - g * S; vv[k] = sm[g * Cp + r * S + s2]; }
+          st4(dst, dst_dt, gi, make_float4(vv[0], vv[1], vv[2], vv[3]));
+        } else {
+          const int g = c / S, s2 = c - g * S;
+          stf(dst, dst_dt, gi, sm[g * Cp + r * S + s2]);
+        }
       }
     }
   }
@@ -397,7 +452,11 @@ extern "C" int vmgb_layernorm(const void* x, int x_dt, void* out, int out_dt, co
   if (!x || !out || !gamma || !beta || !dt_ok(x_dt) || !dt_ok(out_dt) || C <= 0 || C > 32 * MAXV || rows <= 0) return VMGB_EINVAL;
   long long blocks = (rows + 7) / 8;
   const bool vec = (C & 3) == 0 && !((uintptr_t)x & 15) && !((uintptr_t)out & 15) && !((uintptr_t)gamma & 15) && !((uintptr_t)beta & 15);
-  if (vec) layernorm_vec_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, x_dt, out, out_dt, (const float*)gamma, (const float*)beta, rows, C, eps);
+  if (vec && C <= 128) {
+    const long long wanted = (rows + 8 * 4 - 1) / (8 * 4);
+    const unsigned nb = (unsigned)(wanted < 148 * 8 ? (wanted < 1 ? 1 : wanted) : 148 * 8);
+    layernorm_narrow_kernel<4><<<nb, 256, 0, as_stream(stream)>>>(x, x_dt, out, out_dt, (const float*)gamma, (const float*)beta, rows, C, eps);
+  } else if (vec) layernorm_vec_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, x_dt, out, out_dt, (const float*)gamma, (const float*)beta, rows, C, eps);
   else
   layernorm_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, x_dt, out, out_dt, (const float*)gamma, (const float*)beta, rows, C, eps);
   return check_launch();
@@ -426,7 +485,11 @@ extern "C" int vmgb_morph_permute(const void* src, int src_dt, void* dst, int ds
     const long long n_blocks = (long long)BT * O * (Lp / chunk);
     const long long grid = (n_blocks + warps - 1) / warps;
     if (grid > 2147483647LL) return VMGB_EINVAL;
-    morph_block_kernel<<<(unsigned)grid, 32 * warps, smem, as_stream(stream)>>>(src, src_dt, dst, dst_dt, BT, H, W, C, chunk, axis,
+    const bool vec = (C & 3) == 0 && (Cp & 3) == 0 && !(((uintptr_t)src | (uintptr_t)dst) & 15);
+    if (vec) morph_block_kernel<true><<<(unsigned)grid, 32 * warps, smem, as_stream(stream)>>>(src, src_dt, dst, dst_dt, BT, H, W, C, chunk, axis,
+                                                                                               inverse, n_blocks);
+    else
+    morph_block_kernel<false><<<(unsigned)grid, 32 * warps, smem, as_stream(stream)>>>(src, src_dt, dst, dst_dt, BT, H, W, C, chunk, axis,
                                                                                       inverse, n_blocks);
     return check_launch();
   }
