@@ -337,38 +337,41 @@ __device__ __forceinline__ void run_epilogue(const TcP& p, float* bias_s, uint32
     }
   };
   if (reg_res) load_regs(first, cur);
-  const uint32_t res_s0 = smem_u32(bias_s) + 1024;          // two buffers of p.res_smem bytes after the bias
-  auto issue_residual = [&](long long t, int buf) {
-    if (t < total) {
-      int combo, img, hh, ww; bool pvalid;
-      decode(t, row, combo, img, hh, ww, pvalid);
-      const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
-      const long long pix = ((long long)img * p.H + hh) * p.W + ww;
-      for (int ch = half; ch < nchunks; ch += 2) {
-        if (pre_ok(p, pvalid, g, nt * p.NT + ch * 16)) {
-          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_pitch + g * p.Cout_g + nt * p.NT + ch * 16;
-          const uint32_t dst = res_s0 + buf * p.res_smem + (ch * 128 + row) * 32;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rp) : "memory");
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(rp + 8) : "memory");
-        }
-      }
+  const uint32_t res_s0 = smem_u32(bias_s) + 1024;          // ONE staging buffer of p.res_smem bytes after the bias
+  // cp.async of one 32-byte cell (chunk ch of this thread's row) of item t; every thread reads a cell of the
+  // current item BEFORE it re-fills the same cell for the next item, so a single buffer is enough
+  auto issue_cell = [&](bool ok, long long pix, int g, int nt, int ch) {
+    if (ok) {
+      const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_pitch + g * p.Cout_g + nt * p.NT + ch * 16;
+      const uint32_t dst = res_s0 + (ch * 128 + row) * 32;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rp) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(rp + 8) : "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  if (stage_res) issue_residual(first, 0);
+  if (stage_res && first < total) {
+    int combo, img, hh, ww; bool pvalid;
+    decode(first, row, combo, img, hh, ww, pvalid);
+    const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+    const long long pix = ((long long)img * p.H + hh) * p.W + ww;
+    for (int ch = half; ch < nchunks; ch += 2) issue_cell(pre_ok(p, pvalid, g, nt * p.NT + ch * 16), pix, g, nt, ch);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (long long t = first; t < total; t += step, ++it) {
     const int as = it & 1;
     int combo, img, hh, ww; bool pvalid;
     decode(t, row, combo, img, hh, ww, pvalid);
     const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
     const long long pix = ((long long)img * p.H + hh) * p.W + ww;
+    // next item (for the residual refill)
+    const bool has_next = stage_res && t + step < total;
+    int ncombo_ = 0, nimg = 0, nhh = 0, nww = 0; bool npvalid = false;
+    if (has_next) decode(t + step, row, ncombo_, nimg, nhh, nww, npvalid);
+    const int nnt = ncombo_ % p.nt_per_g, ng = ncombo_ / p.nt_per_g;
+    const long long npix = ((long long)nimg * p.H + nhh) * p.W + nww;
     const uint32_t aph = as ? acc_phase1 : acc_phase0;
     if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_STRIDE;
-    if (stage_res) {
-      issue_residual(t + step, (it + 1) & 1);                             // next item's residual, one item ahead
-      asm volatile("cp.async.wait_group 1;" ::: "memory");               // this item's residual has landed
-    }
+    if (stage_res) asm volatile("cp.async.wait_all;" ::: "memory");       // this item's residual (issued one item ago) has landed
     if (reg_res) load_regs(t + step, nxt);
     if (combo != bias_combo) {                                            // bias of this (group, N tile) -> smem
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -388,16 +391,20 @@ __device__ __forceinline__ void run_epilogue(const TcP& p, float* bias_s, uint32
       tmem_ld16(taddr + ch * 16, raw);
       uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
       const bool hp = (stage_res || reg_res) && pre_ok(p, pvalid, g, nt * p.NT + ch * 16);
-      if (hp && stage_res) {
-        const uint32_t src = res_s0 + (it & 1) * p.res_smem + (ch * 128 + row) * 32;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(src));
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(src + 16));
+      if (stage_res) {
+        if (hp) {
+          const uint32_t src = res_s0 + (ch * 128 + row) * 32;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(src) : "memory");
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(src + 16) : "memory");
+        }
+        if (has_next) issue_cell(pre_ok(p, npvalid, ng, nnt * p.NT + ch * 16), npix, ng, nnt, ch);   // refill for the next item
       } else if (hp) {
         const bool second = ch >= half + 2;
         r0 = second ? cur[1][0] : cur[0][0]; r1 = second ? cur[1][1] : cur[0][1];
       }
       epilogue_chunk(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, r0, r1);
     }
+    if (stage_res) asm volatile("cp.async.commit_group;" ::: "memory");
     tc_fence_before();
     mbar_arrive(tempty0 + 8 * as);
     if (reg_res) {
@@ -948,7 +955,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       const int nts = (((Cout_g + sl - 1) / sl) + 15) / 16 * 16;
       if (nts > 256) continue;
       int resb = (epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0) ? nts * 256 : 0;
-      int ra = (budget - nboxes * nts * 128 - 2 * resb) / (18 * 8 * 128);
+      int ra = (budget - nboxes * nts * 128 - resb) / (18 * 8 * 128);
       if (ra >= 2) { best_slices = sl; best_nt = nts; best_ra = ra > 6 ? 6 : ra; best_res = resb; }
     }
     const long long ctas = g_num_sms / (groups * (best_slices ? best_slices : 1));
@@ -979,7 +986,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       }
       const int ncombo = groups * p.nt_per_g;
       long long per = n_mt < ctas ? n_mt : ctas;
-      const int smem = p.ra * p.a_unit_bytes + nboxes * p.b_stage_bytes + 1024 + 512 + 1024 + 2 * p.res_smem;
+      const int smem = p.ra * p.a_unit_bytes + nboxes * p.b_stage_bytes + 1024 + 512 + 1024 + p.res_smem;
       conv3x3_ws_kernel<<<(unsigned)(per * ncombo), TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
       return check_launch();
     }
@@ -1010,9 +1017,9 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
     const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
     // residual staging (2 buffers of 128 rows x NT bf16) when it leaves at least 4 pipeline stages
     p.res_smem = 0;
-    if (epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0 && (budget - 2 * p.NT * 256) / stage_bytes >= 4)
+    if (epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0 && (budget - p.NT * 256) / stage_bytes >= 4)
       p.res_smem = p.NT * 256;
-    p.stages = (budget - 2 * p.res_smem) / stage_bytes;
+    p.stages = (budget - p.res_smem) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return VMGB_EUNSUPPORTED;
   }
@@ -1055,7 +1062,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
     const int smem = p.ra * p.a_unit_bytes + p.rb * p.b_stage_bytes + 1024 + 512 + 1024;
     conv3x3_tc_kernel<false><<<(unsigned)grid, 256, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
   } else {
-    const int smem = p.stages * (A_STAGE_BYTES + p.b_stage_bytes) + 1024 + 512 + 1024 + 2 * p.res_smem;
+    const int smem = p.stages * (A_STAGE_BYTES + p.b_stage_bytes) + 1024 + 512 + 1024 + p.res_smem;
     conv_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
   }
   return check_launch();
