@@ -159,8 +159,9 @@ int vmgb_ltam_wins(const void* q, const void* keys, const void* vals, int dt, lo
 
 /* ---- resampling (layers.py:777-798): pixel-(un)shuffle gather + LayerNorm fused; Linear follows.
  * down: x[BT,H,W,C] -> out[BT,H/2,W/2,4C] feature (neiw,neih,c);  up: x[BT,H,W,C] -> out[BT,2H,2W,C/4].
- * `add` (may be NULL) is summed to x first (skip adds of vmg.py:530-543). */
-int vmgb_resample_ln(const void* x, const void* add, int dt, void* out, int out_dt, const void* gamma, const void* beta,
+ * `add` (may be NULL) is summed to x first (skip adds of vmg.py:530-543).  out rows are out_pitch elements apart
+ * (>= feature count; a multiple of 8 lets the following Linear read them through TMA). */
+int vmgb_resample_ln(const void* x, const void* add, int dt, void* out, int out_dt, int out_pitch, const void* gamma, const void* beta,
                      int BT, int H, int W, int C, int up, float eps, void* stream);
 
 /* ---- mdsc shortcut pieces (vmg.py:389-400,519,525) */

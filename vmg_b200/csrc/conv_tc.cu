@@ -29,7 +29,8 @@ struct TcP {
   int act; float alpha, out_scale; int epi; float res_scale; int ps;
   int b_stage_bytes;
   int nsub, ra, rb, a_unit_bytes, a_sbo;       // 3x3 kernel (conv3x3_tc_kernel) only
-  int res_smem;                                // per-tap kernel: bytes of ONE residual staging buffer (0 = off)
+  int res_smem;                                // bytes of the residual staging buffer (0 = off)
+  int out_smem;                                // bytes of the output staging tile [128][NT+8] bf16 (0 = direct stores)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -108,6 +109,14 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred != 0;
 }
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -155,15 +164,36 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return q;
 }
 
+// exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|erf error| <= 1.5e-7, far below bf16 resolution) on
+// the two single-instruction SFU approximations rcp.approx / ex2.approx: 2 MUFU + ~10 FMA per element.  The FFN
+// fc1 epilogue evaluates ~4e9 GELUs per clip and was ALU-bound on the branchy ~40-instruction erff().
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float erf_abs = fmaf(-poly, e, 1.f);               // erf(|x|/sqrt2)
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);                      // 0.5*x*(1 + sign(x)*erf_abs) = hx + |hx|*erf_abs
+}
+
 // whether chunk `nb` (first column inside the group) of this pixel can use the vector bf16 residual prefetch
 __device__ __forceinline__ bool pre_ok(const TcP& p, bool pvalid, int g, int nb) {
   return pvalid && p.epi != VMGB_EPI_STORE && p.res_dt == VMGB_BF16 && p.ps == 0 && nb + 16 <= p.Cout_g &&
          (((g * p.Cout_g + nb) | p.res_pitch) & 7) == 0;
 }
 
+// ACT / EPI / PS are compile-time for the combinations the model uses (-1 = read from the parameters): the fully
+// generic body is ~2 000 instructions per chunk and thrashed the instruction cache (stall_no_inst); a
+// specialised instance is ~150.
+template <int ACT, int EPI, int PS>
 __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw, bool pvalid, int img, int hh, int ww,
                                                long long pix, int g, int nt, int ch, const float* bias_s, bool have_pre,
-                                               const uint4& pre0, const uint4& pre1) {
+                                               const uint4& pre0, const uint4& pre1, uint32_t out_s = 0u, int row = 0) {
+  const int act = ACT < 0 ? p.act : ACT;
+  const int epi = EPI < 0 ? p.epi : EPI;
+  const int ps = PS < 0 ? p.ps : PS;
   const int nb = nt * p.NT + ch * 16;            // first column of the chunk inside the group
   if (!pvalid || nb >= p.Cout_g) return;
   const int nvalid = min(16, p.Cout_g - nb);
@@ -176,7 +206,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw
     v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b4.z; v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b4.w;
   }
   // one warp-uniform switch per chunk (a per-element switch compiles to 16 jump-table branches)
-  switch (p.act) {
+  switch (act) {
     case VMGB_ACT_RELU:
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -187,7 +217,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw
       break;
     case VMGB_ACT_GELU:
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
+      for (int j = 0; j < 16; ++j) v[j] = gelu_erf_fast(v[j]);
       break;
     case VMGB_ACT_SIGMOID:
 #pragma unroll
@@ -199,7 +229,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] *= p.out_scale;
   }
-  if (p.ps == 2) {
+  if (ps == 2) {
     // co = 4*c + 2*dy + dx  ->  out[(img, 2h+dy, 2w+dx), c]; 16 columns = 4 channels x 4 sub-pixels
     const int c0 = co0 >> 2;
 #pragma unroll
@@ -212,7 +242,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw
     return;
   }
   const long long ob = pix * p.out_pitch + co0;
-  if (p.epi != VMGB_EPI_STORE) {
+  if (epi != VMGB_EPI_STORE) {
     const long long rb = pix * p.res_pitch + co0;
     float r[16], a[16];
     if (have_pre) {
@@ -224,7 +254,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw
 #pragma unroll
       for (int j = 0; j < 16; ++j) r[j] = j < nvalid ? ldf(p.res, p.res_dt, rb + j) : 0.f;
     }
-    if (p.epi == VMGB_EPI_GATE) {
+    if (epi == VMGB_EPI_GATE) {
       const long long ab = pix * p.aux_pitch + co0;
       if (nvalid == 16 && ((p.aux_pitch | co0) & 3) == 0) {
 #pragma unroll
@@ -240,7 +270,12 @@ __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw
       for (int j = 0; j < 16; ++j) v[j] = r[j] + p.res_scale * v[j];
     }
   }
-  if (nvalid == 16 && p.out_dt == VMGB_BF16 && ((p.out_pitch | co0) & 7) == 0) {
+  if (out_s) {      // staged tile: [128 rows][NT + 8] bf16, copied out with coalesced 16-byte stores after the drain
+    const uint4 lo = pack8(v), hi = pack8(v + 8);
+    const uint32_t dst = out_s + (uint32_t)(row * (p.NT + 8) + ch * 16) * 2u;
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+  } else if (nvalid == 16 && p.out_dt == VMGB_BF16 && ((p.out_pitch | co0) & 7) == 0) {
     uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ob);
     o[0] = pack8(v); o[1] = pack8(v + 8);
   } else if (nvalid == 16 && ((p.out_pitch | co0) & 3) == 0) {
@@ -294,7 +329,7 @@ __device__ __forceinline__ void epilogue_tile(const TcP& p, float* bias_s, int& 
     __syncwarp();
     tmem_ld16(tmem_acc + ch * 16, raw);
     const bool hp = i < MAX_PRE && pre_ok(p, pvalid, g, nt * p.NT + ch * 16);
-    epilogue_chunk(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, pre[i < MAX_PRE ? i : 0][0], pre[i < MAX_PRE ? i : 0][1]);
+    epilogue_chunk<-1, -1, -1>(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, pre[i < MAX_PRE ? i : 0][0], pre[i < MAX_PRE ? i : 0][1]);
   }
 }
 
@@ -305,18 +340,20 @@ __device__ __forceinline__ void epilogue_tile(const TcP& p, float* bias_s, int& 
 // cp.async ONE ITEM AHEAD (double buffer [chunk][128 rows][16 bf16], each thread touches only its own cells),
 // so the L2 round trip of the residual read rides under the previous drain instead of stalling this one.
 // ---------------------------------------------------------------------------------------------
-template <class Decode>
-__device__ __forceinline__ void run_epilogue(const TcP& p, float* bias_s, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
-                                             long long first, long long step, long long total, int warp, int lane, Decode decode) {
+template <int ACT, int EPI, int PS, class Decode>
+__device__ __forceinline__ void run_epilogue_t(const TcP& p, float* bias_s, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                               long long first, long long step, long long total, int warp, int lane, Decode decode) {
   const int ew = warp - 4, quarter = warp & 3, half = ew >> 2;
   const int row = quarter * 32 + lane;
   const int nchunks = p.NT >> 4;
   uint32_t acc_phase0 = 0, acc_phase1 = 0;
   int it = 0, bias_combo = -1;
-  const bool stage_res = p.res_smem > 0 && p.epi != VMGB_EPI_STORE;
+  const int epi = EPI < 0 ? p.epi : EPI;
+  const int ps_ = PS < 0 ? p.ps : PS;
+  const bool stage_res = p.res_smem > 0 && epi != VMGB_EPI_STORE;
   // without smem staging (weight-stationary kernel short of shared memory): same one-item-ahead idea in registers,
   // for up to 2 chunks per thread (NT <= 64)
-  const bool reg_res = !stage_res && p.epi != VMGB_EPI_STORE && p.res_dt == VMGB_BF16 && p.ps == 0 && nchunks <= 4;
+  const bool reg_res = !stage_res && epi != VMGB_EPI_STORE && p.res_dt == VMGB_BF16 && ps_ == 0 && nchunks <= 4;
   uint4 cur[2][2], nxt[2][2];
   auto load_regs = [&](long long t, uint4 (&dst)[2][2]) {
 #pragma unroll
@@ -338,6 +375,7 @@ __device__ __forceinline__ void run_epilogue(const TcP& p, float* bias_s, uint32
   };
   if (reg_res) load_regs(first, cur);
   const uint32_t res_s0 = smem_u32(bias_s) + 1024;          // ONE staging buffer of p.res_smem bytes after the bias
+  const uint32_t out_s = p.out_smem > 0 ? res_s0 + p.res_smem : 0u;   // output staging tile after it
   // cp.async of one 32-byte cell (chunk ch of this thread's row) of item t; every thread reads a cell of the
   // current item BEFORE it re-fills the same cell for the next item, so a single buffer is enough
   auto issue_cell = [&](bool ok, long long pix, int g, int nt, int ch) {
@@ -384,11 +422,8 @@ __device__ __forceinline__ void run_epilogue(const TcP& p, float* bias_s, uint32
     }
     mbar_wait(tfull0 + 8 * as, aph);
     tc_fence_after();
-#pragma unroll 1
-    for (int ch = half; ch < nchunks; ch += 2) {
-      uint32_t raw[16];
-      __syncwarp();
-      tmem_ld16(taddr + ch * 16, raw);
+    // drain, software-pipelined over chunks: the tcgen05.ld of chunk c+2 is in flight while chunk c is processed
+    auto process = [&](int ch, const uint32_t* raw) {
       uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
       const bool hp = (stage_res || reg_res) && pre_ok(p, pvalid, g, nt * p.NT + ch * 16);
       if (stage_res) {
@@ -402,17 +437,76 @@ __device__ __forceinline__ void run_epilogue(const TcP& p, float* bias_s, uint32
         const bool second = ch >= half + 2;
         r0 = second ? cur[1][0] : cur[0][0]; r1 = second ? cur[1][1] : cur[0][1];
       }
-      epilogue_chunk(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, r0, r1);
+      epilogue_chunk<ACT, EPI, PS>(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, r0, r1, out_s, row);
+    };
+    {
+      uint32_t rawA[16], rawB[16];
+      int ch = half;
+      __syncwarp();
+      if (ch < nchunks) tmem_ld16_issue(taddr + ch * 16, rawA);
+#pragma unroll 1
+      while (ch < nchunks) {
+        tmem_ld_wait();                                            // rawA ready
+        __syncwarp();
+        if (ch + 2 < nchunks) tmem_ld16_issue(taddr + (ch + 2) * 16, rawB);
+        process(ch, rawA);
+        ch += 2;
+        if (ch >= nchunks) break;
+        tmem_ld_wait();                                            // rawB ready
+        __syncwarp();
+        if (ch + 2 < nchunks) tmem_ld16_issue(taddr + (ch + 2) * 16, rawA);
+        process(ch, rawB);
+        ch += 2;
+      }
     }
     if (stage_res) asm volatile("cp.async.commit_group;" ::: "memory");
     tc_fence_before();
     mbar_arrive(tempty0 + 8 * as);
+    if (out_s) {
+      // cooperative copy-out: consecutive threads write consecutive 16-byte pieces of a pixel's channel run
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int vec_per_row = p.NT >> 3;
+      const int tid = ew * 32 + lane;
+      for (int idx = tid; idx < 128 * vec_per_row; idx += 256) {
+        const int r = idx / vec_per_row, vcol = (idx - r * vec_per_row) * 8;
+        int c2, i2, h2, w2; bool ok2;
+        decode(t, r, c2, i2, h2, w2, ok2);
+        if (ok2 && nt * p.NT + vcol + 8 <= p.Cout_g) {
+          uint4 val;
+          const uint32_t src = out_s + (uint32_t)(r * (p.NT + 8) + vcol) * 2u;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(src) : "memory");
+          const long long o = (((long long)i2 * p.H + h2) * p.W + w2) * p.out_pitch + g * p.Cout_g + nt * p.NT + vcol;
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = val;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // staging tile free for the next item
+    }
     if (reg_res) {
 #pragma unroll
       for (int i = 0; i < 2; ++i) { cur[i][0] = nxt[i][0]; cur[i][1] = nxt[i][1]; }
     }
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// one warp-uniform dispatch per launch onto the specialised epilogue instances
+template <class Decode>
+__device__ __forceinline__ void run_epilogue(const TcP& p, float* bias_s, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                             long long first, long long step, long long total, int warp, int lane, Decode decode) {
+#define VMGB_EPI_CASE(A, E, P)                                                                                          \
+  if (p.act == (A) && p.epi == (E) && p.ps == (P)) {                                                                   \
+    run_epilogue_t<A, E, P>(p, bias_s, tmem_base, tfull0, tempty0, first, step, total, warp, lane, decode);            \
+    return;                                                                                                            \
+  }
+  VMGB_EPI_CASE(VMGB_ACT_NONE, VMGB_EPI_RESADD, 0)     // resblock conv2, FFN fc2, LTAM proj
+  VMGB_EPI_CASE(VMGB_ACT_RELU, VMGB_EPI_STORE, 0)      // resblock conv1, Morph-FC linears
+  VMGB_EPI_CASE(VMGB_ACT_LRELU, VMGB_EPI_STORE, 0)     // trajectory input conv / fusion, HRconv
+  VMGB_EPI_CASE(VMGB_ACT_GELU, VMGB_EPI_STORE, 0)      // FFN fc1
+  VMGB_EPI_CASE(VMGB_ACT_NONE, VMGB_EPI_STORE, 0)      // resampling linears, RCAB conv2, conv_last
+  VMGB_EPI_CASE(VMGB_ACT_NONE, VMGB_EPI_GATE, 0)       // TAB proj + gate
+  VMGB_EPI_CASE(VMGB_ACT_LRELU, VMGB_EPI_STORE, 2)     // upconv + pixel shuffle
+#undef VMGB_EPI_CASE
+  run_epilogue_t<-1, -1, -1>(p, bias_s, tmem_base, tfull0, tempty0, first, step, total, warp, lane, decode);
 }
 
 constexpr int TC_THREADS = 384;      // warps 0-3: producer / MMA / TMEM alloc / spare ; warps 4-11: epilogue
@@ -942,7 +1036,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   p.bias = (const float*)bias; p.out = out; p.res = res; p.aux = aux;
   p.out_dt = out_dt; p.out_pitch = out_pitch; p.res_dt = res_dt; p.res_pitch = res_pitch; p.aux_dt = aux_dt; p.aux_pitch = aux_pitch;
   p.act = act; p.alpha = act_alpha; p.out_scale = out_scale; p.epi = epi; p.res_scale = res_scale; p.ps = pixel_shuffle;
-  p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0; p.res_smem = 0;
+  p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0; p.res_smem = 0; p.out_smem = 0;
   const int budget = g_smem_optin - 1024 - 512 - 1024;     // alignment slack, barriers, bias staging
 
   // ---- weight-stationary 3x3 kernel (variant 8, or auto when the launch is large enough to amortise the
@@ -1019,7 +1113,12 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
     p.res_smem = 0;
     if (epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0 && (budget - p.NT * 256) / stage_bytes >= 4)
       p.res_smem = p.NT * 256;
-    p.stages = (budget - p.res_smem) / stage_bytes;
+    // output staging (coalesced copy-out): bf16 output, 16-byte aligned channel runs, whole-vector validity
+    p.out_smem = 0;
+    if (out_dt == VMGB_BF16 && pixel_shuffle == 0 && (out_pitch & 7) == 0 && (Cout_g & 7) == 0 && !(reinterpret_cast<uintptr_t>(out) & 15) &&
+        (budget - p.res_smem - 128 * (p.NT + 8) * 2) / stage_bytes >= 4)
+      p.out_smem = 128 * (p.NT + 8) * 2;
+    p.stages = (budget - p.res_smem - p.out_smem) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return VMGB_EUNSUPPORTED;
   }
@@ -1062,7 +1161,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
     const int smem = p.ra * p.a_unit_bytes + p.rb * p.b_stage_bytes + 1024 + 512 + 1024;
     conv3x3_tc_kernel<false><<<(unsigned)grid, 256, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
   } else {
-    const int smem = p.stages * (A_STAGE_BYTES + p.b_stage_bytes) + 1024 + 512 + 1024 + p.res_smem;
+    const int smem = p.stages * (A_STAGE_BYTES + p.b_stage_bytes) + 1024 + 512 + 1024 + p.res_smem + p.out_smem;
     conv_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
   }
   return check_launch();

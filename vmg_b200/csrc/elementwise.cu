@@ -356,7 +356,7 @@ __global__ void decay_kernel(float* __restrict__ w, const float* __restrict__ g,
 // ---------------------------------------------------------------------------------------------
 // resampling gather + LayerNorm (layers.py:777-798): one warp per OUTPUT row
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) resample_ln_kernel(const void* x, const void* add, int dt, void* out, int out_dt,
+__global__ void __launch_bounds__(256) resample_ln_kernel(const void* x, const void* add, int dt, void* out, int out_dt, int out_pitch,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           int BT, int H, int W, int C, int up, float eps) {
   const int lane = threadIdx.x & 31;
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(256) resample_ln_kernel(const void* x, const v
   for (int i = 0; i < MAXV; ++i) { const int f = lane + 32 * i; const float d = f < F ? v[i] - mean : 0.f; q += d * d; }
   const float rstd = rsqrtf(warp_sum(q) / (float)F + eps);
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) { const int f = lane + 32 * i; if (f < F) stf(out, out_dt, row * F + f, (v[i] - mean) * rstd * gamma[f] + beta[f]); }
+  for (int i = 0; i < MAXV; ++i) { const int f = lane + 32 * i; if (f < F) stf(out, out_dt, row * out_pitch + f, (v[i] - mean) * rstd * gamma[f] + beta[f]); }
 }
 
 __global__ void maxpool4_kernel(const void* x, int dt, void* out, int out_dt, int BT, int H, int W, int C, long long total) {
@@ -555,14 +555,14 @@ extern "C" int vmgb_decay_weights(float* w, const float* gamma, long long n, voi
   return check_launch();
 }
 
-extern "C" int vmgb_resample_ln(const void* x, const void* add, int dt, void* out, int out_dt, const void* gamma,
+extern "C" int vmgb_resample_ln(const void* x, const void* add, int dt, void* out, int out_dt, int out_pitch, const void* gamma,
                                 const void* beta, int BT, int H, int W, int C, int up, float eps, void* stream) {
   if (!x || !out || !gamma || !beta || !dt_ok(dt) || !dt_ok(out_dt)) return VMGB_EINVAL;
   if (up ? (C & 3) : ((H & 1) || (W & 1))) return VMGB_EINVAL;
   const int F = up ? C / 4 : 4 * C;
-  if (F > 32 * MAXV) return VMGB_EINVAL;
+  if (F > 32 * MAXV || out_pitch < F) return VMGB_EINVAL;
   const long long rows = up ? (long long)BT * 4 * H * W : (long long)BT * (H / 2) * (W / 2);
-  resample_ln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(x, add, dt, out, out_dt, (const float*)gamma,
+  resample_ln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(x, add, dt, out, out_dt, out_pitch, (const float*)gamma,
                                                                                (const float*)beta, BT, H, W, C, up, eps);
   return check_launch();
 }

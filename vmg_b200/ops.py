@@ -209,7 +209,11 @@ def linear(x, pc, **kw):
     rows = 1
     for s in lead:
         rows *= s
-    xv = x.reshape(1, 1, rows, x.shape[-1])
+    if x.is_contiguous():
+        xv = x.reshape(1, 1, rows, x.shape[-1])
+    else:                                   # rows uniformly `pitch` elements apart (channel slice of a wider buffer)
+        _, pitch = _pix(x)
+        xv = x.as_strided((1, 1, rows, x.shape[-1]), (0, 0, pitch, 1))
     for k in ('res', 'aux', 'out'):
         if kw.get(k) is not None:
             kw[k] = kw[k].reshape(1, 1, rows, kw[k].shape[-1])
@@ -321,8 +325,11 @@ def resample_ln(x, add_, gamma, beta, up, eps=1e-5):
     N, H, W, C = x.shape
     assert x.is_contiguous() and (add_ is None or (add_.is_contiguous() and add_.shape == x.shape))
     shape = (N, 2 * H, 2 * W, C // 4) if up else (N, H // 2, W // 2, 4 * C)
-    out = torch.empty(shape, device=x.device, dtype=x.dtype)
-    _ck(lib().vmgb_resample_ln(x.data_ptr(), _ptr(add_), _dt(x), out.data_ptr(), _dt(out), gamma.data_ptr(),
+    F_ = shape[-1]
+    pitch = -(-F_ // 8) * 8                      # rows padded to 16 bytes (bf16) so the next Linear can use TMA
+    buf = torch.empty(shape[:-1] + (pitch,), device=x.device, dtype=x.dtype)
+    out = buf[..., :F_]
+    _ck(lib().vmgb_resample_ln(x.data_ptr(), _ptr(add_), _dt(x), out.data_ptr(), _dt(out), pitch, gamma.data_ptr(),
                                beta.data_ptr(), N, H, W, C, int(up), eps, _stream()), 'vmgb_resample_ln')
     return out
 
