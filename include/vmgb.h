@@ -100,9 +100,9 @@ int vmgb_layernorm(const void* x, int x_dt, void* out, int out_dt, const void* g
 /* ---- Morph-FC chunk permutation (function.py:763-785, closed form SURVEY.md A.2) -------------
  * axis 0 = H branch, 1 = W branch.  inverse=0: x[BT,H,W,C] -> A[rows, Cp] (zero padded rows/channels);
  * inverse=1: Y[rows, Cp] -> y[BT,H,W,C] (cropped).  Cp = ceil(C/chunk)*chunk,
- * rows = BT * ceil(L/chunk)*chunk * other, L = H (axis 0) or W (axis 1). */
+ * rows = BT * ceil(L/chunk)*chunk * other, L = H (axis 0) or W (axis 1); matrix rows are a_pitch (>= Cp) elements apart. */
 int vmgb_morph_permute(const void* src, int src_dt, void* dst, int dst_dt,
-                       int BT, int H, int W, int C, int chunk, int axis, int inverse, void* stream);
+                       int BT, int H, int W, int C, int chunk, int axis, int inverse, int a_pitch, void* stream);
 
 /* ---- grouped channel sums (fp32 out, must be zeroed by the caller).  function.py:791 (TAB global
  * mean over T,H,W per sample), :546-558 (CALayer per-frame pool).  Rows are laid out as

@@ -73,10 +73,15 @@ def linear(x, pc, **kw):
     for s in lead:
         rows *= s
     xv = x.reshape(1, 1, rows, x.shape[-1])
-    for k in ('res', 'aux', 'out'):
+    out = kw.pop('out', None)
+    for k in ('res', 'aux'):
         if kw.get(k) is not None:
             kw[k] = kw[k].reshape(1, 1, rows, kw[k].shape[-1])
-    return conv2d(xv, pc, **kw).reshape(*lead, pc.Cout)
+    y = conv2d(xv, pc, **kw).reshape(*lead, pc.Cout)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
 
 
 def layernorm(x, gamma, beta, out_dtype=None, eps=1e-5):

@@ -47,6 +47,8 @@ def main():
     lines.append(f'| **total** | {sum(v[0] for v in agg.values())} | {tot / 1e3:.2f} | | |')
     text = '\n'.join(lines)
     print(text)
+    from vmg_b200 import ops
+    print('bf16 launches on the generic kernel:', sorted(set(ops.FALLBACK_LOG)))
     if a.out:
         open(a.out, 'w').write(text + '\n')
 

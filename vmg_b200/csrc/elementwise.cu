@@ -183,7 +183,7 @@ __global__ void morph_scatter_kernel(const void* Y, int y_dt, void* out, int out
 constexpr int MORPH_WARPS = 4;
 template <bool VEC>
 __global__ void __launch_bounds__(32 * MORPH_WARPS) morph_block_kernel(const void* src, int src_dt, void* dst, int dst_dt, int BT, int H,
-                                                                      int W, int C, int ch, int axis, int inverse, long long n_blocks) {
+                                                                      int W, int C, int ch, int axis, int inverse, long long n_blocks, int a_pitch) {
   extern __shared__ float sm_all[];
   const int Cp = (C + ch - 1) / ch * ch, S = Cp / ch;
   const int L = axis == 0 ? H : W, Lg = (L + ch - 1) / ch, O = axis == 0 ? W : H;
@@ -218,13 +218,15 @@ __global__ void __launch_bounds__(32 * MORPH_WARPS) morph_block_kernel(const voi
     }
     __syncwarp();
     for (int i = lane; i < ch * Cpv; i += 32) {
-      if (VEC) st4(dst, dst_dt, rows0 * Cp + 4 * i, *reinterpret_cast<const float4*>(sm + 4 * i));
-      else stf(dst, dst_dt, rows0 * Cp + i, sm[i]);
+      const int rr = (V * i) / Cp, cc = (V * i) - rr * Cp;
+      if (VEC) st4(dst, dst_dt, (rows0 + rr) * a_pitch + cc, *reinterpret_cast<const float4*>(sm + 4 * i));
+      else stf(dst, dst_dt, (rows0 + rr) * a_pitch + cc, sm[i]);
     }
   } else {
     for (int i = lane; i < ch * Cpv; i += 32) {
-      if (VEC) *reinterpret_cast<float4*>(sm + 4 * i) = ld4(src, src_dt, rows0 * Cp + 4 * i);
-      else sm[i] = ldf(src, src_dt, rows0 * Cp + i);
+      const int rr = (V * i) / Cp, cc = (V * i) - rr * Cp;
+      if (VEC) *reinterpret_cast<float4*>(sm + 4 * i) = ld4(src, src_dt, (rows0 + rr) * a_pitch + cc);
+      else sm[i] = ldf(src, src_dt, (rows0 + rr) * a_pitch + cc);
     }
     __syncwarp();
     for (int i = lane; i < ch * Cv; i += 32) {
@@ -473,9 +475,10 @@ extern "C" int vmgb_l2norm(const void* x, int x_dt, int x_pitch, void* out, int 
 }
 
 extern "C" int vmgb_morph_permute(const void* src, int src_dt, void* dst, int dst_dt, int BT, int H, int W, int C, int chunk,
-                                  int axis, int inverse, void* stream) {
+                                  int axis, int inverse, int a_pitch, void* stream) {
   if (!src || !dst || !dt_ok(src_dt) || !dt_ok(dst_dt) || chunk <= 0 || (axis != 0 && axis != 1)) return VMGB_EINVAL;
   const int Cp = (C + chunk - 1) / chunk * chunk;
+  if (a_pitch < Cp) return VMGB_EINVAL;
   const int L = axis == 0 ? H : W, Lp = (L + chunk - 1) / chunk * chunk, O = axis == 0 ? W : H;
   const size_t per_warp = (size_t)chunk * Cp * sizeof(float);
   int warps = (int)((48 * 1024) / per_warp);
@@ -485,14 +488,15 @@ extern "C" int vmgb_morph_permute(const void* src, int src_dt, void* dst, int ds
     const long long n_blocks = (long long)BT * O * (Lp / chunk);
     const long long grid = (n_blocks + warps - 1) / warps;
     if (grid > 2147483647LL) return VMGB_EINVAL;
-    const bool vec = (C & 3) == 0 && (Cp & 3) == 0 && !(((uintptr_t)src | (uintptr_t)dst) & 15);
+    const bool vec = (C & 3) == 0 && (Cp & 3) == 0 && (a_pitch & 3) == 0 && !(((uintptr_t)src | (uintptr_t)dst) & 15);
     if (vec) morph_block_kernel<true><<<(unsigned)grid, 32 * warps, smem, as_stream(stream)>>>(src, src_dt, dst, dst_dt, BT, H, W, C, chunk, axis,
-                                                                                               inverse, n_blocks);
+                                                                                               inverse, n_blocks, a_pitch);
     else
     morph_block_kernel<false><<<(unsigned)grid, 32 * warps, smem, as_stream(stream)>>>(src, src_dt, dst, dst_dt, BT, H, W, C, chunk, axis,
-                                                                                      inverse, n_blocks);
+                                                                                      inverse, n_blocks, a_pitch);
     return check_launch();
   }
+  if (a_pitch != Cp) return VMGB_EUNSUPPORTED;
   if (!inverse) {
     long long total = (long long)BT * Lp * O * Cp;
     morph_gather_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(src, src_dt, dst, dst_dt, BT, H, W, C, chunk, axis, total);

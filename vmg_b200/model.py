@@ -359,7 +359,8 @@ class VMG(nn.Module):
                                                         (sm.mlp_w[0], sm.gamma_w, sm.chunk_w, sm.Cw))):
             o.decay_weights_(lin.weight.data, gamma)                     # function.py:765-768 / 778-781
             A = o.morph_gather(xn, chunk, axis)
-            Y = o.linear(A, self._pc(lin, force=True), act=o.ACT_RELU, out_scale=1.0 / Cp)
+            Y = torch.empty_strided(A.shape, A.stride(), device=A.device, dtype=A.dtype)   # same (16-byte padded) row pitch
+            o.linear(A, self._pc(lin, force=True), act=o.ACT_RELU, out_scale=1.0 / Cp, out=Y)
             branches.append(o.morph_scatter(Y, N, H, W, C, chunk, axis))
             del A, Y
         h, w = branches

@@ -150,6 +150,9 @@ def pack_conv(weight, bias, groups=1, tc=False):
     return pc
 
 
+FALLBACK_LOG = []
+
+
 def tc_supported(pc, xs, n_src):
     """Shapes the tcgen05 kernel takes (see csrc/conv_tc.cu)."""
     if pc.wtc is None or xs[0].dtype != torch.bfloat16:
@@ -195,6 +198,8 @@ def conv2d(x, pc, act=ACT_NONE, alpha=0.0, out_scale=1.0, epi=EPI_STORE, res=Non
                                       act, alpha, out_scale, epi, res_scale, pixel_shuffle, tc_variant, _stream()),
             'vmgb_conv2d_nhwc_tc')
     else:
+        if xs[0].dtype == torch.bfloat16 and len(FALLBACK_LOG) < 64:      # diagnostics: bf16 launches that missed the tcgen05 path
+            FALLBACK_LOG.append((tuple(xs[0].shape), ptrs[0][1], pc.Cin, pc.Cout, pc.R, pc.groups, n_src, use_tc, pc.wtc is not None))
         _ck(lib().vmgb_conv2d_nhwc(ptrs[0][0], p1, p2, n_src, _dt(xs[0]), ptrs[0][1], pc.w32.data_ptr(), bias,
                                    optr, _dt(out), opitch, rptr, rdt, rpitch, aptr, adt, apitch,
                                    N, H, W, pc.Cin, pc.Cout, pc.R, pc.S, pc.groups,
@@ -203,22 +208,27 @@ def conv2d(x, pc, act=ACT_NONE, alpha=0.0, out_scale=1.0, epi=EPI_STORE, res=Non
     return out
 
 
-def linear(x, pc, **kw):
-    """x [..., K] -> [..., N]; a Linear is the 1x1 'conv' over a [1,1,rows,K] image."""
-    lead = x.shape[:-1]
+def _rows_view(t):
+    """[..., C] tensor whose rows are uniformly strided -> [1, 1, rows, C] view sharing its memory."""
     rows = 1
-    for s in lead:
+    for s in t.shape[:-1]:
         rows *= s
-    if x.is_contiguous():
-        xv = x.reshape(1, 1, rows, x.shape[-1])
-    else:                                   # rows uniformly `pitch` elements apart (channel slice of a wider buffer)
-        _, pitch = _pix(x)
-        xv = x.as_strided((1, 1, rows, x.shape[-1]), (0, 0, pitch, 1))
+    if t.is_contiguous():
+        return t.reshape(1, 1, rows, t.shape[-1])
+    _, pitch = _pix(t)
+    return t.as_strided((1, 1, rows, t.shape[-1]), (0, 0, pitch, 1))
+
+
+def linear(x, pc, **kw):
+    """x [..., K] -> [..., N]; a Linear is the 1x1 'conv' over a [1,1,rows,K] image.  x / res / aux / out may be
+    channel slices of wider (pitched) buffers."""
+    lead = x.shape[:-1]
+    out = kw.get('out')
     for k in ('res', 'aux', 'out'):
         if kw.get(k) is not None:
-            kw[k] = kw[k].reshape(1, 1, rows, kw[k].shape[-1])
-    y = conv2d(xv, pc, **kw)
-    return y.reshape(*lead, pc.Cout)
+            kw[k] = _rows_view(kw[k])
+    y = conv2d(_rows_view(x), pc, **kw)
+    return out if out is not None else y.reshape(*lead, pc.Cout)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -250,17 +260,18 @@ def morph_gather(x, chunk, axis):
     Cp = -(-C // chunk) * chunk
     L, O = (H, W) if axis == 0 else (W, H)
     rows = N * (-(-L // chunk) * chunk) * O
-    A = torch.empty((rows, Cp), device=x.device, dtype=x.dtype)
-    _ck(lib().vmgb_morph_permute(x.data_ptr(), _dt(x), A.data_ptr(), _dt(A), N, H, W, C, chunk, axis, 0, _stream()),
+    pitch = -(-Cp // 8) * 8                      # 16-byte rows (bf16) so the Linear can read them through TMA
+    A = torch.empty((rows, pitch), device=x.device, dtype=x.dtype)[:, :Cp]
+    _ck(lib().vmgb_morph_permute(x.data_ptr(), _dt(x), A.data_ptr(), _dt(A), N, H, W, C, chunk, axis, 0, pitch, _stream()),
         'vmgb_morph_permute')
     return A
 
 
 def morph_scatter(Y, N, H, W, C, chunk, axis):
     require_device()
-    assert Y.is_contiguous()
+    assert Y.stride(-1) == 1
     out = torch.empty((N, H, W, C), device=Y.device, dtype=Y.dtype)
-    _ck(lib().vmgb_morph_permute(Y.data_ptr(), _dt(Y), out.data_ptr(), _dt(out), N, H, W, C, chunk, axis, 1, _stream()),
+    _ck(lib().vmgb_morph_permute(Y.data_ptr(), _dt(Y), out.data_ptr(), _dt(out), N, H, W, C, chunk, axis, 1, Y.stride(0), _stream()),
         'vmgb_morph_permute')
     return out
 
