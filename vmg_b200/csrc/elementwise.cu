@@ -394,6 +394,56 @@ __global__ void __launch_bounds__(256) resample_ln_kernel(const void* x, const v
   for (int i = 0; i < MAXV; ++i) { const int f = lane + 32 * i; if (f < F) stf(out, out_dt, row * out_pitch + f, (v[i] - mean) * rstd * gamma[f] + beta[f]); }
 }
 
+// vectorised variant (C % 4 == 0, F % 4 == 0): lane owns features [4*lane + 128*i, +4)
+__global__ void __launch_bounds__(256) resample_ln_vec_kernel(const void* x, const void* add, int dt, void* out, int out_dt, int out_pitch,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              int BT, int H, int W, int C, int up, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int Ho = up ? 2 * H : H / 2, Wo = up ? 2 * W : W / 2, F = up ? C / 4 : 4 * C;
+  if (row >= (long long)BT * Ho * Wo) return;
+  const int wo = (int)(row % Wo); const long long t = row / Wo; const int ho = (int)(t % Ho); const int bt = (int)(t / Ho);
+  float4 v[MAXQ];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i) {
+    const int f = 4 * lane + 128 * i;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f >= F) continue;
+    long long idx;
+    if (!up) {
+      const int q = f / C, c = f - q * C, neiw = q >> 1, neih = q & 1;
+      idx = (((long long)bt * H + (2 * ho + neih)) * W + (2 * wo + neiw)) * C + c;
+    } else {
+      const int neih = ho & 1, neiw = wo & 1;
+      idx = (((long long)bt * H + (ho >> 1)) * W + (wo >> 1)) * C + (neiw * 2 + neih) * F + f;
+    }
+    float4 val = ld4(x, dt, idx);
+    if (add) { const float4 a = ld4(add, dt, idx); val.x += a.x; val.y += a.y; val.z += a.z; val.w += a.w; }
+    v[i] = val;
+    s += (val.x + val.y) + (val.z + val.w);
+  }
+  const float mean = warp_sum(s) / (float)F;
+  float q2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i) {
+    if (4 * lane + 128 * i < F) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c2 = v[i].z - mean, d = v[i].w - mean;
+      q2 += (a * a + b * b) + (c2 * c2 + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q2) / (float)F + eps);
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i) {
+    const int f = 4 * lane + 128 * i;
+    if (f < F) {
+      const float4 g = *reinterpret_cast<const float4*>(gamma + f), b = *reinterpret_cast<const float4*>(beta + f);
+      st4(out, out_dt, row * out_pitch + f, make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                                                        (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w));
+    }
+  }
+}
+
 __global__ void maxpool4_kernel(const void* x, int dt, void* out, int out_dt, int BT, int H, int W, int C, long long total) {
   const int Ho = H / 4, Wo = W / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -566,6 +616,11 @@ extern "C" int vmgb_resample_ln(const void* x, const void* add, int dt, void* ou
   const int F = up ? C / 4 : 4 * C;
   if (F > 32 * MAXV || out_pitch < F) return VMGB_EINVAL;
   const long long rows = up ? (long long)BT * 4 * H * W : (long long)BT * (H / 2) * (W / 2);
+  const bool rvec = (C & 3) == 0 && (F & 3) == 0 && (out_pitch & 3) == 0 && F <= 128 * MAXQ &&
+                    !(((uintptr_t)x | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)add) & 15);
+  if (rvec) resample_ln_vec_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(x, add, dt, out, out_dt, out_pitch, (const float*)gamma,
+                                                                                   (const float*)beta, BT, H, W, C, up, eps);
+  else
   resample_ln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(x, add, dt, out, out_dt, out_pitch, (const float*)gamma,
                                                                                (const float*)beta, BT, H, W, C, up, eps);
   return check_launch();

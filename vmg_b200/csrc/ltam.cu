@@ -78,6 +78,113 @@ __global__ void __launch_bounds__(128) ltam_wins_kernel(const void* q, const voi
         make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv));
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// bf16 variant with shared-memory staging.  A block owns 8 windows; per key frame the 32 gathered key rows
+// and 32 value rows (C bf16 each) are fetched with 16-byte cp.async (coalesced inside a row, double buffered
+// across key frames) and every (head, query) thread then reads its head segment from shared memory.  The
+// direct version above issues 8-byte loads per thread and re-reads each row through L1 for the 4 queries.
+// ---------------------------------------------------------------------------------------------
+template <int D4>
+__global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ keys,
+                                                             const __nv_bfloat16* __restrict__ vals, long long kv_stride,
+                                                             const float* __restrict__ loc, int loc_pitch, const float* __restrict__ rel,
+                                                             const float* __restrict__ decay, void* out, int out_dt, int n, int h, int w,
+                                                             int K, long long n_windows) {
+  constexpr int D = D4 * 4, C = 4 * D, ROWB = C * 2, CH = ROWB / 16;     // bytes / 16-byte chunks per row
+  extern __shared__ __align__(16) uint8_t sm[];                           // [2 stages][2 (k,v)][32 rows][ROWB]
+  const int tid = threadIdx.x;
+  const long long win0 = (long long)blockIdx.x * 8;
+  const int wl = tid >> 4, sub = tid & 15, head = sub >> 2, qi = sub & 3;
+  const long long win = win0 + wl;
+  const bool active = win < n_windows;
+  const int wh = h >> 1, ww = w >> 1;
+  const long long wc = active ? win : n_windows - 1;
+  const int wx = (int)(wc % ww); const long long t0 = wc / ww; const int wy = (int)(t0 % wh); const int img = (int)(t0 / wh);
+  const long long pix0 = ((long long)img * h + 2 * wy) * w + 2 * wx;
+  const long long qpix = pix0 + (qi >> 1) * w + (qi & 1);
+  const float scale = rsqrtf((float)D);
+
+  float qv[D], acc[D];
+#pragma unroll
+  for (int i = 0; i < D4; ++i) {
+    const float4 v = ld4(q, VMGB_BF16, qpix * C + head * D + i * 4);
+    qv[4 * i] = v.x * scale; qv[4 * i + 1] = v.y * scale; qv[4 * i + 2] = v.z * scale; qv[4 * i + 3] = v.w * scale;
+    acc[4 * i] = acc[4 * i + 1] = acc[4 * i + 2] = acc[4 * i + 3] = 0.f;
+  }
+  const float dh = decay[head];
+  float relq[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) relq[j] = rel[(head * 4 + qi) * 4 + j];
+
+  // stage one key frame: 32 rows x CH chunks for keys and the same for values
+  auto stage = [&](int k, int buf) {
+    uint8_t* base = sm + buf * (2 * 32 * ROWB);
+    for (int c = tid; c < 32 * CH; c += 128) {
+      const int r = c / CH, cc = c - r * CH;               // r = window-local row: (window r>>2, position r&3)
+      long long wn = win0 + (r >> 2);
+      if (wn >= n_windows) wn = n_windows - 1;
+      const int x2 = (int)(wn % ww); const long long t2 = wn / ww; const int y2 = (int)(t2 % wh); const int i2 = (int)(t2 / wh);
+      const long long pj = ((long long)i2 * h + 2 * y2 + ((r & 3) >> 1)) * w + 2 * x2 + (r & 1);
+      const float2 lc = *reinterpret_cast<const float2*>(loc + pj * loc_pitch + 2 * k);
+      const int sx = (int)rintf(lc.x), sy = (int)rintf(lc.y);
+      const uint32_t dk = (uint32_t)__cvta_generic_to_shared(base + r * ROWB + cc * 16);
+      const uint32_t dv = dk + 32 * ROWB;
+      if (sx >= 0 && sx < w && sy >= 0 && sy < h) {
+        const long long src = (long long)k * kv_stride + (((long long)i2 * h + sy) * w + sx) * C + cc * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dk), "l"(keys + src) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dv), "l"(vals + src) : "memory");
+      } else {                                              // padding_mode='zeros'
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dk), "r"(0) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dv), "r"(0) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float m = -INFINITY, l = 0.f, pe = 1.f;
+  stage(K - 1, 0);
+  int buf = 0;
+  for (int k = K - 1; k >= 0; --k, buf ^= 1) {
+    if (k > 0) stage(k - 1, buf ^ 1);
+    if (k > 0) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    pe *= dh;
+    const uint8_t* base = sm + buf * (2 * 32 * ROWB);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16* kr = reinterpret_cast<const __nv_bfloat16*>(base + (wl * 4 + j) * ROWB) + head * D;
+      const __nv_bfloat16* vr = kr + 32 * C;
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < D4; ++i) {
+        const float4 kv = ld4(kr, VMGB_BF16, i * 4);
+        dot += kv.x * qv[4 * i] + kv.y * qv[4 * i + 1] + kv.z * qv[4 * i + 2] + kv.w * qv[4 * i + 3];
+      }
+      const float logit = dot + pe * relq[j];
+      const float mn = fmaxf(m, logit);
+      const float corr = __expf(m - mn), pw = __expf(logit - mn);
+      l = l * corr + pw;
+      m = mn;
+#pragma unroll
+      for (int i = 0; i < D4; ++i) {
+        const float4 vv = ld4(vr, VMGB_BF16, i * 4);
+        acc[4 * i] = acc[4 * i] * corr + pw * vv.x;
+        acc[4 * i + 1] = acc[4 * i + 1] * corr + pw * vv.y;
+        acc[4 * i + 2] = acc[4 * i + 2] * corr + pw * vv.z;
+        acc[4 * i + 3] = acc[4 * i + 3] * corr + pw * vv.w;
+      }
+    }
+    __syncthreads();                                        // this buffer is re-filled two iterations later
+  }
+  if (!active) return;
+  const float inv = 1.f / l;
+#pragma unroll
+  for (int i = 0; i < D4; ++i)
+    st4(out, out_dt, qpix * C + head * D + i * 4,
+        make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv));
+}
+
 }  // namespace vmgb
 
 using namespace vmgb;
@@ -90,6 +197,15 @@ extern "C" int vmgb_ltam_wins(const void* q, const void* keys, const void* vals,
   const long long n_windows = (long long)n * (h / 2) * (w / 2);
   const unsigned blocks = (unsigned)((n_windows + 7) / 8);
   const int D4 = C / heads / 4;
+  if (dt == VMGB_BF16 && !(((uintptr_t)keys | (uintptr_t)vals) & 15) && (kv_stride & 7) == 0 && (D4 == 7 || D4 == 9)) {
+    const int smem = 2 * 2 * 32 * C * 2;
+#define LAUNCH_S(DD)                                                                                                          \
+    ltam_wins_smem_kernel<DD><<<blocks, 128, smem, as_stream(stream)>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)keys,  \
+        (const __nv_bfloat16*)vals, kv_stride, loc, loc_pitch, rel, decay, out, out_dt, n, h, w, K, n_windows)
+    if (D4 == 7) LAUNCH_S(7); else LAUNCH_S(9);
+#undef LAUNCH_S
+    return check_launch();
+  }
 #define LAUNCH(DD) ltam_wins_kernel<DD><<<blocks, 128, 0, as_stream(stream)>>>(q, keys, vals, dt, kv_stride, loc, loc_pitch, rel, decay, out, out_dt, n, h, w, C, heads, K, n_windows)
   switch (D4) {
     case 4: LAUNCH(4); break;    // C = 64
