@@ -31,6 +31,7 @@ struct TcP {
   int nsub, ra, rb, a_unit_bytes, a_sbo;       // 3x3 kernel (conv3x3_tc_kernel) only
   int res_smem;                                // bytes of the residual staging buffer (0 = off)
   int out_smem;                                // bytes of the output staging tile [128][NT+8] bf16 (0 = direct stores)
+  int aux_smem;                                // bytes of the gate-operand staging buffer (GATE epilogue; 0 = off)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -190,7 +191,8 @@ __device__ __forceinline__ bool pre_ok(const TcP& p, bool pvalid, int g, int nb)
 template <int ACT, int EPI, int PS>
 __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw, bool pvalid, int img, int hh, int ww,
                                                long long pix, int g, int nt, int ch, const float* bias_s, bool have_pre,
-                                               const uint4& pre0, const uint4& pre1, uint32_t out_s = 0u, int row = 0) {
+                                               const uint4& pre0, const uint4& pre1, uint32_t out_s = 0u, int row = 0,
+                                               bool have_aux = false, const uint4& ax0 = uint4{0, 0, 0, 0}, const uint4& ax1 = uint4{0, 0, 0, 0}) {
   const int act = ACT < 0 ? p.act : ACT;
   const int epi = EPI < 0 ? p.epi : EPI;
   const int ps = PS < 0 ? p.ps : PS;
@@ -256,7 +258,9 @@ __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw
     }
     if (epi == VMGB_EPI_GATE) {
       const long long ab = pix * p.aux_pitch + co0;
-      if (nvalid == 16 && ((p.aux_pitch | co0) & 3) == 0) {
+      if (have_aux) {
+        unpack8(ax0, a); unpack8(ax1, a + 8);
+      } else if (nvalid == 16 && ((p.aux_pitch | co0) & 3) == 0) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) { const float4 t = ld4(p.aux, p.aux_dt, ab + 4 * q); a[4 * q] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w; }
       } else {
@@ -264,7 +268,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw
         for (int j = 0; j < 16; ++j) a[j] = j < nvalid ? ldf(p.aux, p.aux_dt, ab + j) : 0.f;
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = r[j] + p.res_scale * ((a[j] + v[j]) * tanhf(v[j]));
+      for (int j = 0; j < 16; ++j) {
+        float th;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(v[j]));
+        v[j] = r[j] + p.res_scale * ((a[j] + v[j]) * th);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = r[j] + p.res_scale * v[j];
@@ -376,6 +384,8 @@ __device__ __forceinline__ void run_epilogue_t(const TcP& p, float* bias_s, uint
   if (reg_res) load_regs(first, cur);
   const uint32_t res_s0 = smem_u32(bias_s) + 1024;          // ONE staging buffer of p.res_smem bytes after the bias
   const uint32_t out_s = p.out_smem > 0 ? res_s0 + p.res_smem : 0u;   // output staging tile after it
+  const uint32_t aux_s0 = res_s0 + p.res_smem + p.out_smem;            // gate-operand staging after that
+  const bool stage_aux = stage_res && p.aux_smem > 0 && epi == VMGB_EPI_GATE && p.aux_dt == VMGB_BF16 && p.aux_pitch == p.res_pitch;
   // cp.async of one 32-byte cell (chunk ch of this thread's row) of item t; every thread reads a cell of the
   // current item BEFORE it re-fills the same cell for the next item, so a single buffer is enough
   auto issue_cell = [&](bool ok, long long pix, int g, int nt, int ch) {
@@ -384,6 +394,12 @@ __device__ __forceinline__ void run_epilogue_t(const TcP& p, float* bias_s, uint
       const uint32_t dst = res_s0 + (ch * 128 + row) * 32;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rp) : "memory");
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(rp + 8) : "memory");
+      if (stage_aux) {      // same cell of the gate operand (same pitch and alignment as the residual)
+        const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(p.aux) + pix * p.aux_pitch + g * p.Cout_g + nt * p.NT + ch * 16;
+        const uint32_t da = aux_s0 + (ch * 128 + row) * 32;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(ap) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da + 16), "l"(ap + 8) : "memory");
+      }
     }
   };
   if (stage_res && first < total) {
@@ -424,20 +440,25 @@ __device__ __forceinline__ void run_epilogue_t(const TcP& p, float* bias_s, uint
     tc_fence_after();
     // drain, software-pipelined over chunks: the tcgen05.ld of chunk c+2 is in flight while chunk c is processed
     auto process = [&](int ch, const uint32_t* raw) {
-      uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+      uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, a0 = r0, a1 = r0;
       const bool hp = (stage_res || reg_res) && pre_ok(p, pvalid, g, nt * p.NT + ch * 16);
       if (stage_res) {
         if (hp) {
           const uint32_t src = res_s0 + (ch * 128 + row) * 32;
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(src) : "memory");
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(src + 16) : "memory");
+          if (stage_aux) {
+            const uint32_t sa = aux_s0 + (ch * 128 + row) * 32;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a0.x), "=r"(a0.y), "=r"(a0.z), "=r"(a0.w) : "r"(sa) : "memory");
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a1.x), "=r"(a1.y), "=r"(a1.z), "=r"(a1.w) : "r"(sa + 16) : "memory");
+          }
         }
         if (has_next) issue_cell(pre_ok(p, npvalid, ng, nnt * p.NT + ch * 16), npix, ng, nnt, ch);   // refill for the next item
       } else if (hp) {
         const bool second = ch >= half + 2;
         r0 = second ? cur[1][0] : cur[0][0]; r1 = second ? cur[1][1] : cur[0][1];
       }
-      epilogue_chunk<ACT, EPI, PS>(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, r0, r1, out_s, row);
+      epilogue_chunk<ACT, EPI, PS>(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, r0, r1, out_s, row, hp && stage_aux, a0, a1);
     };
     {
       uint32_t rawA[16], rawB[16];
@@ -1036,7 +1057,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   p.bias = (const float*)bias; p.out = out; p.res = res; p.aux = aux;
   p.out_dt = out_dt; p.out_pitch = out_pitch; p.res_dt = res_dt; p.res_pitch = res_pitch; p.aux_dt = aux_dt; p.aux_pitch = aux_pitch;
   p.act = act; p.alpha = act_alpha; p.out_scale = out_scale; p.epi = epi; p.res_scale = res_scale; p.ps = pixel_shuffle;
-  p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0; p.res_smem = 0; p.out_smem = 0;
+  p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0; p.res_smem = 0; p.out_smem = 0; p.aux_smem = 0;
   const int budget = g_smem_optin - 1024 - 512 - 1024;     // alignment slack, barriers, bias staging
 
   // ---- weight-stationary 3x3 kernel (variant 8, or auto when the launch is large enough to amortise the
@@ -1044,20 +1065,27 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   if (R == 3 && S == 3 && H >= 8 && W >= 8 && (variant == 8 || variant == 0)) {
     const int nboxes = n_src * p.kb_per_src * 9;
     const long long n_mt = (long long)n_img * ((H + 15) / 16) * ((W + 7) / 8);
-    int best_slices = 0, best_nt = 0, best_ra = 0, best_res = 0;
+    int best_slices = 0, best_nt = 0, best_ra = 0, best_res = 0, best_out = 0;
     for (int sl = 1; sl <= 8 && !best_slices; ++sl) {
       const int nts = (((Cout_g + sl - 1) / sl) + 15) / 16 * 16;
       if (nts > 256) continue;
-      int resb = (epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0) ? nts * 256 : 0;
-      int ra = (budget - nboxes * nts * 128 - resb) / (18 * 8 * 128);
-      if (ra >= 2) { best_slices = sl; best_nt = nts; best_ra = ra > 6 ? 6 : ra; best_res = resb; }
+      const int resb = (epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0) ? nts * 256 : 0;
+      int left = budget - nboxes * nts * 128 - resb;
+      // coalesced copy-out for wide outputs (FFN hidden tensor): only if the activation ring keeps >= 3 units
+      int outb = 0;
+      if (Cout >= 256 && out_dt == VMGB_BF16 && pixel_shuffle == 0 && (out_pitch & 7) == 0 && (Cout_g & 7) == 0 &&
+          !(reinterpret_cast<uintptr_t>(out) & 15) && (left - 128 * (nts + 8) * 2) / (18 * 8 * 128) >= 3)
+        outb = 128 * (nts + 8) * 2;
+      left -= outb;
+      const int ra = left / (18 * 8 * 128);
+      if (ra >= 2) { best_slices = sl; best_nt = nts; best_ra = ra > 6 ? 6 : ra; best_res = resb; best_out = outb; }
     }
     const long long ctas = g_num_sms / (groups * (best_slices ? best_slices : 1));
     // auto: measured wins (tools/microbench.py) are the single-source, ungrouped convs with <= 2 K blocks
     // (trajectory resblocks at C=112, recon head); at least ~4 M tiles per CTA amortise the resident weight load
     const bool worth = best_slices && ctas >= 1 && n_mt >= 4 * ctas && n_src == 1 && groups == 1 && p.kb_per_src <= 2;
     if (best_slices && ctas >= 1 && (variant == 8 || worth)) {
-      p.nt_per_g = best_slices; p.NT = best_nt; p.b_stage_bytes = best_nt * 128; p.ra = best_ra; p.res_smem = best_res;
+      p.nt_per_g = best_slices; p.NT = best_nt; p.b_stage_bytes = best_nt * 128; p.ra = best_ra; p.res_smem = best_res; p.out_smem = best_out;
       p.BH = 16; p.BW = 8; p.a_unit_bytes = 18 * 8 * 128; p.stages = 0;
       p.tiles_h = (H + 15) / 16; p.tiles_w = (W + 7) / 8;
       p.total_tiles = n_mt * groups * p.nt_per_g;
@@ -1080,7 +1108,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       }
       const int ncombo = groups * p.nt_per_g;
       long long per = n_mt < ctas ? n_mt : ctas;
-      const int smem = p.ra * p.a_unit_bytes + nboxes * p.b_stage_bytes + 1024 + 512 + 1024 + p.res_smem;
+      const int smem = p.ra * p.a_unit_bytes + nboxes * p.b_stage_bytes + 1024 + 512 + 1024 + p.res_smem + p.out_smem;
       conv3x3_ws_kernel<<<(unsigned)(per * ncombo), TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
       return check_launch();
     }
@@ -1118,7 +1146,11 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
     if (out_dt == VMGB_BF16 && pixel_shuffle == 0 && (out_pitch & 7) == 0 && (Cout_g & 7) == 0 && !(reinterpret_cast<uintptr_t>(out) & 15) &&
         (budget - p.res_smem - 128 * (p.NT + 8) * 2) / stage_bytes >= 4)
       p.out_smem = 128 * (p.NT + 8) * 2;
-    p.stages = (budget - p.res_smem - p.out_smem) / stage_bytes;
+    p.aux_smem = 0;
+    if (epi == VMGB_EPI_GATE && p.res_smem && aux_dt == VMGB_BF16 && aux_pitch == res_pitch && !(reinterpret_cast<uintptr_t>(aux) & 15) &&
+        (budget - p.res_smem - p.out_smem - p.NT * 256) / stage_bytes >= 3)
+      p.aux_smem = p.NT * 256;
+    p.stages = (budget - p.res_smem - p.out_smem - p.aux_smem) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return VMGB_EUNSUPPORTED;
   }
@@ -1161,7 +1193,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
     const int smem = p.ra * p.a_unit_bytes + p.rb * p.b_stage_bytes + 1024 + 512 + 1024;
     conv3x3_tc_kernel<false><<<(unsigned)grid, 256, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
   } else {
-    const int smem = p.stages * (A_STAGE_BYTES + p.b_stage_bytes) + 1024 + 512 + 1024 + p.res_smem + p.out_smem;
+    const int smem = p.stages * (A_STAGE_BYTES + p.b_stage_bytes) + 1024 + 512 + 1024 + p.res_smem + p.out_smem + p.aux_smem;
     conv_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
   }
   return check_launch();
