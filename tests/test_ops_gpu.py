@@ -118,6 +118,15 @@ def test_conv3x3_variants(case, variant):
     close(out, ref, 2e-3)
 
 
+@pytest.mark.parametrize('case', [(2, 24, 24, 8, 32, 7, 1, ops.ACT_RELU, ops.EPI_STORE, 0, 1), (2, 12, 20, 64, 32, 7, 1, ops.ACT_RELU, ops.EPI_STORE, 0, 1),
+                                  (1, 20, 20, 16, 2, 7, 1, ops.ACT_NONE, ops.EPI_RESADD, 0, 1), (3, 33, 41, 32, 64, 7, 1, ops.ACT_RELU, ops.EPI_STORE, 0, 1)],
+                         ids=lambda c: 'x'.join(map(str, c)))
+def test_conv7x7_weight_stationary(case):
+    N, H, W, Cin, Cout, R, groups, act, epi, ps, n_src = case
+    out, ref = conv_case(N, H, W, Cin, Cout, R, groups, torch.bfloat16, True, n_src, act, epi, ps, out_dtype=torch.float32, variant=8)
+    close(out, ref, 2e-3)
+
+
 def test_conv_tcgen05_many_tiles_persistent():
     # more tiles than SMs -> exercises the smem ring wrap-around and both TMEM accumulators
     out, ref = conv_case(6, 64, 64, 144, 144, 3, 1, torch.bfloat16, True, 1, ops.ACT_RELU, ops.EPI_RESADD, 0, out_dtype=torch.float32)

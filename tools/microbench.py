@@ -49,6 +49,10 @@ def conv_cases():
         ('conv_last_64to3', 2, 720, 1280, 64, 3, 3, 1, 1, ops.EPI_STORE, ops.ACT_NONE, 0),
         ('spynet_8to32_7x7', 99, 192, 320, 8, 32, 7, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
         ('spynet_32to64_7x7', 99, 192, 320, 32, 64, 7, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
+        ('spynet_64to32_7x7', 99, 192, 320, 64, 32, 7, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
+        ('spynet_32to16_7x7', 99, 192, 320, 32, 16, 7, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
+        ('spynet_16to2_7x7', 99, 192, 320, 16, 2, 7, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
+        ('spynet_8to32_7x7_l3', 99, 24, 40, 8, 32, 7, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
     ]
 
 
@@ -66,7 +70,7 @@ def run_conv(iters, only=None, variants=(0,)):
         o = torch.empty(oshape, device=DEV, dtype=torch.float32 if Cout == 3 else torch.bfloat16)
         res = torch.randn(oshape, device=DEV).bfloat16() if epi != ops.EPI_STORE else None
         for variant in variants:
-            if variant > 1 and R != 3:
+            if (1 < variant < 8 and R != 3) or (variant == 8 and R not in (3, 7)):
                 continue
             fn = lambda: ops.conv2d(xs if n_src > 1 else xs[0], pc, act=act, alpha=0.1, epi=epi, res=res, res_scale=0.1, pixel_shuffle=ps, out=o, tc_variant=variant)
             try:

@@ -836,7 +836,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
 
 // ---------------------------------------------------------------------------------------------
-// 3x3 convolution, WEIGHT-STATIONARY variant (the trajectory resblock convs: 63-67 % of all FLOPs).
+// RxR (3x3 / 7x7) convolution, WEIGHT-STATIONARY variant (the trajectory resblock convs: 63-67 % of all FLOPs; SPyNet).
 // Measured on B200: the per-tap kernel is bound by the L2 -> SM fabric (~9 TB/s aggregate, ~60 GB/s per SM),
 // moving 484 KB per 128-pixel tile at C = N = 112, of which 226 KB are the same weights again and again.
 // Here the output channels of a group are split into `nt_per_g` slices of NT columns and every CTA keeps the
@@ -847,12 +847,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 // Work split: CTA b owns combo = b % (groups*slices) for the whole launch and walks the M tiles
 // b / ncombo, b / ncombo + grid / ncombo, ...
 // ---------------------------------------------------------------------------------------------
+template <int RR>      // square odd kernel size: 3 or 7 (compile-time so that the MMA issue loop stays tight)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_ws_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB, const TcP p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int nboxes = p.n_src * p.kb_per_src * 9;
+  constexpr int TAPS = RR * RR, UROWS = 16 + RR - 1, PADR = RR / 2;
+  const int nboxes = p.n_src * p.kb_per_src * TAPS;
   const uint32_t a_base = smem_base;
   const uint32_t w_base = a_base + p.ra * p.a_unit_bytes;
   const uint32_t bar_base = w_base + nboxes * p.b_stage_bytes;
@@ -894,13 +896,13 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       mbar_expect_tx(wfull, (uint32_t)(nboxes * p.NT * 128));
       for (int src = 0; src < p.n_src; ++src)
         for (int kb = 0; kb < p.kb_per_src; ++kb)
-          for (int tap = 0; tap < 9; ++tap)
-            tma_load_2d(w_base + ((src * p.kb_per_src + kb) * 9 + tap) * p.b_stage_bytes, &mapB, wfull, src * p.Cs + kb * 64,
-                        (g * 9 + tap) * p.Cout_g + nt * p.NT);
+          for (int tap = 0; tap < TAPS; ++tap)
+            tma_load_2d(w_base + ((src * p.kb_per_src + kb) * TAPS + tap) * p.b_stage_bytes, &mapB, wfull, src * p.Cs + kb * 64,
+                        (g * TAPS + tap) * p.Cout_g + nt * p.NT);
     }
     __syncwarp();
     int ia = 0; uint32_t pa = 0;
-    const uint32_t a_bytes = 18 * 8 * 128;
+    const uint32_t a_bytes = (uint32_t)UROWS * 8 * 128;
     for (long long mt = first; mt < n_mt; mt += step) {
       const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
       const int h0 = (rem / p.tiles_w) * 16, w0 = (rem % p.tiles_w) * 8;
@@ -908,11 +910,11 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const CUtensorMap* mA = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
         for (int kb = 0; kb < p.kb_per_src; ++kb) {
           const int ca = (p.n_src > 1 ? 0 : ((g * p.Cin_g) & ~7)) + kb * 64;
-          for (int sft = 0; sft < 3; ++sft) {
+          for (int sft = 0; sft < RR; ++sft) {
             mbar_wait(aempty0 + 8 * ia, pa ^ 1);
             if (elect_one()) {
               mbar_expect_tx(afull0 + 8 * ia, a_bytes);
-              tma_load_4d(a_base + ia * p.a_unit_bytes, mA, afull0 + 8 * ia, ca, w0 + sft - 1, h0 - 1, img);
+              tma_load_4d(a_base + ia * p.a_unit_bytes, mA, afull0 + 8 * ia, ca, w0 + sft - PADR, h0 - PADR, img);
             }
             __syncwarp();
             if (++ia == p.ra) { ia = 0; pa ^= 1; }
@@ -941,19 +943,19 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         for (int kb = 0; kb < p.kb_per_src; ++kb) {
           const int nks = min(4, (kext - kb * 64 + 15) >> 4);
           const bool last_kb = src == p.n_src - 1 && kb == p.kb_per_src - 1;
-          for (int sft = 0; sft < 3; ++sft) {
+          for (int sft = 0; sft < RR; ++sft) {
             mbar_wait(afull0 + 8 * ia, pa);
             tc_fence_after();
             const uint32_t a_unit = a_base + ia * p.a_unit_bytes;
             if (elect_one()) {
-              for (int r = 0; r < 3; ++r) {
+              for (int r = 0; r < RR; ++r) {
                 const uint64_t ad = smem_desc_sw128(a_unit + (uint32_t)r * 1024u);
-                const uint64_t bd = smem_desc_sw128(w_base + ((src * p.kb_per_src + kb) * 9 + r * 3 + sft) * p.b_stage_bytes);
+                const uint64_t bd = smem_desc_sw128(w_base + ((src * p.kb_per_src + kb) * TAPS + r * RR + sft) * p.b_stage_bytes);
                 for (int ks = 0; ks < nks; ++ks)
                   umma_f16(d_tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)((r | ks) > 0));
               }
               umma_commit(aempty0 + 8 * ia);
-              if (last_kb && sft == 2) umma_commit(tfull0 + 8 * as);
+              if (last_kb && sft == RR - 1) umma_commit(tfull0 + 8 * as);
             }
             __syncwarp();
             accumulate = 1;
@@ -1007,7 +1009,8 @@ static void tc_init() {
     cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
     cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
     cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-    cudaFuncSetAttribute(conv3x3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+    cudaFuncSetAttribute(conv3x3_ws_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+    cudaFuncSetAttribute(conv3x3_ws_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
   }
 }
 
@@ -1062,8 +1065,9 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
 
   // ---- weight-stationary 3x3 kernel (variant 8, or auto when the launch is large enough to amortise the
   //      one-off weight load): find the smallest number of output-channel slices whose weights fit
-  if (R == 3 && S == 3 && H >= 8 && W >= 8 && (variant == 8 || variant == 0)) {
-    const int nboxes = n_src * p.kb_per_src * 9;
+  if (R == S && (R == 3 || R == 7) && H >= 8 && W >= 8 && (variant == 8 || variant == 0)) {
+    const int urows = 16 + R - 1, ubytes = urows * 8 * 128;
+    const int nboxes = n_src * p.kb_per_src * R * R;
     const long long n_mt = (long long)n_img * ((H + 15) / 16) * ((W + 7) / 8);
     int best_slices = 0, best_nt = 0, best_ra = 0, best_res = 0, best_out = 0;
     for (int sl = 1; sl <= 8 && !best_slices; ++sl) {
@@ -1074,19 +1078,20 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       // coalesced copy-out for wide outputs (FFN hidden tensor): only if the activation ring keeps >= 3 units
       int outb = 0;
       if (Cout >= 256 && out_dt == VMGB_BF16 && pixel_shuffle == 0 && (out_pitch & 7) == 0 && (Cout_g & 7) == 0 &&
-          !(reinterpret_cast<uintptr_t>(out) & 15) && (left - 128 * (nts + 8) * 2) / (18 * 8 * 128) >= 3)
+          !(reinterpret_cast<uintptr_t>(out) & 15) && (left - 128 * (nts + 8) * 2) / ubytes >= 3)
         outb = 128 * (nts + 8) * 2;
       left -= outb;
-      const int ra = left / (18 * 8 * 128);
+      const int ra = left / ubytes;
       if (ra >= 2) { best_slices = sl; best_nt = nts; best_ra = ra > 6 ? 6 : ra; best_res = resb; best_out = outb; }
     }
     const long long ctas = g_num_sms / (groups * (best_slices ? best_slices : 1));
     // auto: measured wins (tools/microbench.py) are the single-source, ungrouped convs with <= 2 K blocks
     // (trajectory resblocks at C=112, recon head); at least ~4 M tiles per CTA amortise the resident weight load
-    const bool worth = best_slices && ctas >= 1 && n_mt >= 4 * ctas && n_src == 1 && groups == 1 && p.kb_per_src <= 2;
+    const bool worth = best_slices && ctas >= 1 && n_mt >= 4 * ctas && n_src == 1 && groups == 1 && p.kb_per_src <= 2 &&
+                       (R == 3 || Cin <= 32);      // 7x7: measured wins only where the 64-wide K block is mostly padding
     if (best_slices && ctas >= 1 && (variant == 8 || worth)) {
       p.nt_per_g = best_slices; p.NT = best_nt; p.b_stage_bytes = best_nt * 128; p.ra = best_ra; p.res_smem = best_res; p.out_smem = best_out;
-      p.BH = 16; p.BW = 8; p.a_unit_bytes = 18 * 8 * 128; p.stages = 0;
+      p.BH = 16; p.BW = 8; p.a_unit_bytes = ubytes; p.stages = 0;
       p.tiles_h = (H + 15) / 16; p.tiles_w = (W + 7) / 8;
       p.total_tiles = n_mt * groups * p.nt_per_g;
       CUtensorMap mA[3], mB;
@@ -1097,11 +1102,11 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
         if (reinterpret_cast<uintptr_t>(ptr) & 15) return VMGB_EINVAL;
         cuuint64_t dims[4] = {(cuuint64_t)c_extent, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
         cuuint64_t str[3] = {(cuuint64_t)x_pitch * 2, (cuuint64_t)W * x_pitch * 2, (cuuint64_t)H * W * x_pitch * 2};
-        cuuint32_t box[4] = {64, 8, 18, 1};
+        cuuint32_t box[4] = {64, 8, (cuuint32_t)urows, 1};
         if (!encode_bf16(&mA[s], ptr, 4, dims, str, box)) return VMGB_EINVAL;
       }
       {
-        cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)groups * 9 * Cout_g};
+        cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)groups * R * R * Cout_g};
         cuuint64_t str[1] = {(cuuint64_t)Kp * 2};
         cuuint32_t box[2] = {64, (cuuint32_t)p.NT};
         if (!encode_bf16(&mB, w, 2, dims, str, box)) return VMGB_EINVAL;
@@ -1109,7 +1114,8 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       const int ncombo = groups * p.nt_per_g;
       long long per = n_mt < ctas ? n_mt : ctas;
       const int smem = p.ra * p.a_unit_bytes + nboxes * p.b_stage_bytes + 1024 + 512 + 1024 + p.res_smem + p.out_smem;
-      conv3x3_ws_kernel<<<(unsigned)(per * ncombo), TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
+      if (R == 3) conv3x3_ws_kernel<3><<<(unsigned)(per * ncombo), TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
+      else conv3x3_ws_kernel<7><<<(unsigned)(per * ncombo), TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
       return check_launch();
     }
     if (variant == 8) return VMGB_EUNSUPPORTED;

@@ -159,6 +159,8 @@ def tc_supported(pc, xs, n_src):
         return False
     if n_src > 1 and (pc.Cin // n_src) % 16:
         return False
+    if pc.R > 1 and (xs[0].shape[1] < 8 or xs[0].shape[2] < 8):
+        return False        # images smaller than a tile (coarsest SPyNet levels): TMA boxes would be mostly out of bounds
     return all(_pix(x)[1] % 8 == 0 and x.data_ptr() % 16 == 0 for x in xs)
 
 
