@@ -40,6 +40,7 @@ def conv_cases():
         ('traj_in_224to112', 1, 184, 320, 224, 112, 3, 1, 2, ops.EPI_STORE, ops.ACT_LRELU, 0),
         ('traj_res_112_b2', 2, 184, 320, 112, 112, 3, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
         ('traj_res_112_b4', 4, 184, 320, 112, 112, 3, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
+        ('traj_res_112_b4_store', 4, 184, 320, 112, 112, 3, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
         ('ffn_fc1_g4_112', 25, 184, 320, 112, 672, 3, 4, 1, ops.EPI_STORE, ops.ACT_GELU, 0),
         ('ffn_fc2_672to112', 1, 1, 25 * 184 * 320, 672, 112, 1, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
         ('linear_112', 1, 1, 25 * 184 * 320, 112, 112, 1, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
@@ -69,8 +70,12 @@ def run_conv(iters, only=None, variants=(0,)):
         oshape = (N, 2 * H, 2 * W, Cout // 4) if ps else (N, H, W, Cout)
         o = torch.empty(oshape, device=DEV, dtype=torch.float32 if Cout == 3 else torch.bfloat16)
         res = torch.randn(oshape, device=DEV).bfloat16() if epi != ops.EPI_STORE else None
+        ref = None
+        if len(variants) > 1:            # cross-check every variant against the per-tap kernel
+            ops.conv2d(xs if n_src > 1 else xs[0], pc, act=act, alpha=0.1, epi=epi, res=res, res_scale=0.1, pixel_shuffle=ps, out=o, tc_variant=1)
+            ref = o.float().clone()
         for variant in variants:
-            if (1 < variant < 8 and R != 3) or (variant == 8 and R not in (3, 7)):
+            if (1 < variant < 8 and R != 3) or (variant == 8 and R not in (3, 7)) or (variant > 8 and R != 3):
                 continue
             fn = lambda: ops.conv2d(xs if n_src > 1 else xs[0], pc, act=act, alpha=0.1, epi=epi, res=res, res_scale=0.1, pixel_shuffle=ps, out=o, tc_variant=variant)
             try:
@@ -80,6 +85,8 @@ def run_conv(iters, only=None, variants=(0,)):
                 continue
             fl = 2.0 * N * H * W * Cout * R * R * (Cin // groups)
             rec = {'case': name, 'variant': variant, 'ms': round(ms, 4), 'tflops': round(fl / ms / 1e9, 1), 'gflop': round(fl / 1e9, 2)}
+            if ref is not None:
+                rec['maxdiff_vs_v1'] = float((o.float() - ref).abs().max())
             print(json.dumps(rec), flush=True)
             out.append(rec)
     return out

@@ -7,15 +7,17 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 SRCS="api.cu conv_generic.cu conv_tc.cu elementwise.cu warp.cu ltam.cu"
 mkdir -p build
 OBJS=""
+PIDS=""
 for s in $SRCS; do
   [ -f "$s" ] || continue
   o=build/${s%.cu}.o
   if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ../../include/vmgb.h -nt "$o" ]; then
     echo "nvcc $s"
     $NVCC $FLAGS ${VMGB_PTXAS_V:+-Xptxas -v} -c "$s" -o "$o" &
+    PIDS="$PIDS $!"
   fi
   OBJS="$OBJS $o"
 done
-wait
+for pid in $PIDS; do wait "$pid" || { echo "nvcc failed" >&2; rm -f ../libvmgb.so; exit 1; }; done
 $NVCC -shared -gencode arch=compute_100a,code=sm_100a -cudart static -o ../libvmgb.so $OBJS -ldl -lpthread -lrt
 echo "built $(cd .. && pwd)/libvmgb.so"

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <cstdlib>
 
 namespace vmgb {
 
@@ -28,10 +29,12 @@ struct TcP {
   int out_dt, out_pitch, res_dt, res_pitch, aux_dt, aux_pitch;
   int act; float alpha, out_scale; int epi; float res_scale; int ps;
   int b_stage_bytes;
-  int nsub, ra, rb, a_unit_bytes, a_sbo;       // 3x3 kernel (conv3x3_tc_kernel) only
+  int nsub, ra, rb, a_unit_bytes, a_sbo;       // weight-stationary kernels: ra = activation ring depth, a_unit_bytes = unit stride
   int res_smem;                                // bytes of the residual staging buffer (0 = off)
   int out_smem;                                // bytes of the output staging tile [128][NT+8] bf16 (0 = direct stores)
   int aux_smem;                                // bytes of the gate-operand staging buffer (GATE epilogue; 0 = off)
+  int wst;                                     // 1 = warp-private transposition staging epilogue (run_epilogue_w), 32 KB
+  int dbg;                                     // bottleneck probes (tools/microbench.py): 1 = no MMA, 2 = no drain, 4 = no activation loads
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -58,7 +61,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) break;
-    if (++spins > (1u << 26)) __trap();     // a lost arrival becomes an error, never a hang
+    if (++spins > (1u << 21)) __trap();     // a lost arrival becomes an error (after a few seconds: try_wait itself blocks for a while), never a hang
   }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -90,6 +93,55 @@ __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// ---- CTA-pair (cta_group::2) forms: one MMA spans the two SMs of a TPC (M = 256), each CTA holds its own 128
+// rows of A and HALF of the B rows; barriers of the pair live in the leader CTA (rank 0)
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  // default .release.cta semantics (what the accumulator hand-back needs after tcgen05.fence::before_thread_sync);
+  // .release.cluster compiles to MEMBAR.ALL.GPU, which waits for every global store of the epilogue still in flight
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// predicated forms: the surrounding code stays warp-uniform (descriptors in uniform registers, no R2UR per operand);
+// `issue` is this lane's elect.sync result
+__device__ __forceinline__ void umma_f16_2sm_if(uint32_t issue, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_if(uint32_t issue, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"(mask), "r"(issue) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -132,6 +184,12 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
          ((uint64_t)2 << 61);
 }
 
+// SWIZZLE_32B, K-major operand of exactly one K = 16 slice: rows of 32 B, 8-row groups 256 B apart
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)6 << 61);
+}
+
 constexpr int A_STAGE_BYTES = 128 * 128;   // 128 pixels x 64 bf16
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;            // column offset of the second accumulator
@@ -145,7 +203,6 @@ constexpr int ACC_STRIDE = 256;            // column offset of the second accumu
 //   2. reads the bias from shared memory (staged once per (group, N tile)),
 //   3. tcgen05.ld -> bias / activation / scale / residual / gate / pixel shuffle -> 16-byte stores.
 // ---------------------------------------------------------------------------------------------
-constexpr int MAX_PRE = 8;       // chunks per thread whose residual is prefetched (8 warps x 8 = NT 256 at most... x2 halves)
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
@@ -191,7 +248,7 @@ __device__ __forceinline__ bool pre_ok(const TcP& p, bool pvalid, int g, int nb)
 template <int ACT, int EPI, int PS>
 __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw, bool pvalid, int img, int hh, int ww,
                                                long long pix, int g, int nt, int ch, const float* bias_s, bool have_pre,
-                                               const uint4& pre0, const uint4& pre1, uint32_t out_s = 0u, int row = 0,
+                                               const uint4& pre0, const uint4& pre1, uint32_t sdst0 = 0u, uint32_t sdst1 = 0u,
                                                bool have_aux = false, const uint4& ax0 = uint4{0, 0, 0, 0}, const uint4& ax1 = uint4{0, 0, 0, 0}) {
   const int act = ACT < 0 ? p.act : ACT;
   const int epi = EPI < 0 ? p.epi : EPI;
@@ -278,11 +335,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw
       for (int j = 0; j < 16; ++j) v[j] = r[j] + p.res_scale * v[j];
     }
   }
-  if (out_s) {      // staged tile: [128 rows][NT + 8] bf16, copied out with coalesced 16-byte stores after the drain
+  if ((p.dbg & 8) && !sdst0) { if (v[0] + v[5] + v[10] + v[15] == 123.456f) stf(p.out, p.out_dt, ob, v[3]); return; }     // probe: no stores
+  if (sdst0) {      // staged in shared memory (two 16-byte pieces), copied out with coalesced 16-byte stores after the drain
     const uint4 lo = pack8(v), hi = pack8(v + 8);
-    const uint32_t dst = out_s + (uint32_t)(row * (p.NT + 8) + ch * 16) * 2u;
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sdst0), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sdst1), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
   } else if (nvalid == 16 && p.out_dt == VMGB_BF16 && ((p.out_pitch | co0) & 7) == 0) {
     uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ob);
     o[0] = pack8(v); o[1] = pack8(v + 8);
@@ -295,52 +352,6 @@ __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw
   }
 }
 
-// One accumulator (sub-tile) of one tile, executed by all EPI_WARPS epilogue warps.
-//   ew: epilogue warp index 0..EPI_WARPS-1 ; lane quarter = ew & 3 ; chunk phase = ew >> 2
-template <int EPI_WARPS>
-__device__ __forceinline__ void epilogue_tile(const TcP& p, float* bias_s, int& bias_combo, int combo, int ew, int lane, uint32_t tmem_acc,
-                                              int img, int hh, int ww, bool pvalid, int g, int nt, uint32_t tfull_bar, uint32_t parity,
-                                              bool wait_full) {
-  constexpr int STEP = EPI_WARPS / 4;
-  const int nchunks = p.NT >> 4;
-  const int half = ew >> 2;
-  const long long pix = ((long long)img * p.H + hh) * p.W + ww;
-  // 1. residual prefetch (registers), issued before the accumulator is complete
-  uint4 pre[MAX_PRE][2];
-#pragma unroll
-  for (int i = 0; i < MAX_PRE; ++i) {
-    const int ch = half + STEP * i;
-    pre[i][0] = make_uint4(0, 0, 0, 0); pre[i][1] = make_uint4(0, 0, 0, 0);
-    if (ch < nchunks && pre_ok(p, pvalid, g, nt * p.NT + ch * 16)) {
-      const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_pitch + g * p.Cout_g + nt * p.NT + ch * 16;
-      pre[i][0] = ldg_nc_v4(rp); pre[i][1] = ldg_nc_v4(rp + 8);
-    }
-  }
-  // 2. bias of this (group, N tile) -> smem, once per change of combo
-  if (combo != bias_combo) {
-    asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");          // previous readers are done
-    const int t = ew * 32 + lane;
-    for (int c = t; c < p.NT; c += EPI_WARPS * 32) {
-      const int nb = nt * p.NT + c;
-      bias_s[c] = (p.bias && nb < p.Cout_g) ? __ldg(p.bias + g * p.Cout_g + nb) : 0.f;
-    }
-    asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
-    bias_combo = combo;
-  }
-  if (wait_full) { mbar_wait(tfull_bar, parity); tc_fence_after(); }
-  // 3. drain
-#pragma unroll
-  for (int i = 0; i < 16 / STEP; ++i) {
-    const int ch = half + STEP * i;
-    if (ch >= nchunks) break;
-    uint32_t raw[16];
-    __syncwarp();
-    tmem_ld16(tmem_acc + ch * 16, raw);
-    const bool hp = i < MAX_PRE && pre_ok(p, pvalid, g, nt * p.NT + ch * 16);
-    epilogue_chunk<-1, -1, -1>(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, pre[i < MAX_PRE ? i : 0][0], pre[i < MAX_PRE ? i : 0][1]);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
 // Epilogue driver of the 384-thread kernels (8 epilogue warps).  `decode(t, row, combo, img, hh, ww, pvalid)`
@@ -350,7 +361,8 @@ __device__ __forceinline__ void epilogue_tile(const TcP& p, float* bias_s, int& 
 // ---------------------------------------------------------------------------------------------
 template <int ACT, int EPI, int PS, class Decode>
 __device__ __forceinline__ void run_epilogue_t(const TcP& p, float* bias_s, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
-                                               long long first, long long step, long long total, int warp, int lane, Decode decode) {
+                                               long long first, long long step, long long total, int warp, int lane, Decode decode,
+                                               uint32_t tempty_cluster0) {
   const int ew = warp - 4, quarter = warp & 3, half = ew >> 2;
   const int row = quarter * 32 + lane;
   const int nchunks = p.NT >> 4;
@@ -438,6 +450,11 @@ __device__ __forceinline__ void run_epilogue_t(const TcP& p, float* bias_s, uint
     }
     mbar_wait(tfull0 + 8 * as, aph);
     tc_fence_after();
+    if (p.dbg & 2) {
+      tc_fence_before();
+      if (tempty_cluster0) mbar_arrive_cluster(tempty_cluster0 + 8 * as); else mbar_arrive(tempty0 + 8 * as);
+      continue;
+    }
     // drain, software-pipelined over chunks: the tcgen05.ld of chunk c+2 is in flight while chunk c is processed
     auto process = [&](int ch, const uint32_t* raw) {
       uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, a0 = r0, a1 = r0;
@@ -458,7 +475,8 @@ __device__ __forceinline__ void run_epilogue_t(const TcP& p, float* bias_s, uint
         const bool second = ch >= half + 2;
         r0 = second ? cur[1][0] : cur[0][0]; r1 = second ? cur[1][1] : cur[0][1];
       }
-      epilogue_chunk<ACT, EPI, PS>(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, r0, r1, out_s, row, hp && stage_aux, a0, a1);
+      const uint32_t sd = out_s ? out_s + (uint32_t)(row * (p.NT + 8) + ch * 16) * 2u : 0u;      // staged tile [128 rows][NT + 8] bf16
+      epilogue_chunk<ACT, EPI, PS>(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, r0, r1, sd, sd + 16, hp && stage_aux, a0, a1);
     };
     {
       uint32_t rawA[16], rawB[16];
@@ -482,7 +500,8 @@ __device__ __forceinline__ void run_epilogue_t(const TcP& p, float* bias_s, uint
     }
     if (stage_res) asm volatile("cp.async.commit_group;" ::: "memory");
     tc_fence_before();
-    mbar_arrive(tempty0 + 8 * as);
+    if (tempty_cluster0) mbar_arrive_cluster(tempty_cluster0 + 8 * as);     // CTA pair: the leader's MMA warp waits for both epilogues
+    else mbar_arrive(tempty0 + 8 * as);
     if (out_s) {
       // cooperative copy-out: consecutive threads write consecutive 16-byte pieces of a pixel's channel run
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -513,10 +532,11 @@ __device__ __forceinline__ void run_epilogue_t(const TcP& p, float* bias_s, uint
 // one warp-uniform dispatch per launch onto the specialised epilogue instances
 template <class Decode>
 __device__ __forceinline__ void run_epilogue(const TcP& p, float* bias_s, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
-                                             long long first, long long step, long long total, int warp, int lane, Decode decode) {
+                                             long long first, long long step, long long total, int warp, int lane, Decode decode,
+                                             uint32_t tempty_cluster0 = 0) {
 #define VMGB_EPI_CASE(A, E, P)                                                                                          \
   if (p.act == (A) && p.epi == (E) && p.ps == (P)) {                                                                   \
-    run_epilogue_t<A, E, P>(p, bias_s, tmem_base, tfull0, tempty0, first, step, total, warp, lane, decode);            \
+    run_epilogue_t<A, E, P>(p, bias_s, tmem_base, tfull0, tempty0, first, step, total, warp, lane, decode, tempty_cluster0); \
     return;                                                                                                            \
   }
   VMGB_EPI_CASE(VMGB_ACT_NONE, VMGB_EPI_RESADD, 0)     // resblock conv2, FFN fc2, LTAM proj
@@ -527,7 +547,164 @@ __device__ __forceinline__ void run_epilogue(const TcP& p, float* bias_s, uint32
   VMGB_EPI_CASE(VMGB_ACT_NONE, VMGB_EPI_GATE, 0)       // TAB proj + gate
   VMGB_EPI_CASE(VMGB_ACT_LRELU, VMGB_EPI_STORE, 2)     // upconv + pixel shuffle
 #undef VMGB_EPI_CASE
-  run_epilogue_t<-1, -1, -1>(p, bias_s, tmem_base, tfull0, tempty0, first, step, total, warp, lane, decode);
+  run_epilogue_t<-1, -1, -1>(p, bias_s, tmem_base, tfull0, tempty0, first, step, total, warp, lane, decode, tempty_cluster0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue with WARP-PRIVATE transposition staging (bf16 output, no pixel shuffle; STORE, or RESADD with NT <= 128).
+// tcgen05.ld 32x32b hands every thread ONE accumulator row, so a direct epilogue reads the residual and writes
+// the output as 32-byte pieces of 32 different pixels per warp instruction: 32 L1 wavefronts for 1 KB.  Measured
+// on the trajectory resblock conv (probes in tools/microbench.py): 1.9 us (residual) + 1.3 us (stores) per
+// 128 x 112 tile against 0.5 us for TMEM loads + math - the epilogue, not the tensor pipe, paced the kernel.
+// Here each epilogue warp owns a 4 KB buffer = its 32 rows x 64 columns (one "group") of bf16, 16-byte pieces
+// XOR-swizzled by (row & 7) so that both access patterns are bank-conflict free:
+//   coalesced side : lane -> (row = lane/8 + 4i, piece = lane%8); a warp instruction moves 4 rows x 128 contiguous
+//                    bytes (4 wavefronts per 512 B): cp.async of the NEXT item's residual, and the copy-out
+//   row side       : lane -> its own row; reads the residual pieces of a 16-column chunk, writes the result in place
+// No CTA-wide barrier is needed (__syncwarp only) and the buffer is 32 KB per CTA for any NT.
+// `origin(t, combo, img, h0, w0, valid)` maps a work item to its tile; rows map to pixels by the power-of-two BW.
+// ---------------------------------------------------------------------------------------------
+template <int ACT, int EPI, class Origin>
+__device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                                 long long first, long long step, long long total, int warp, int lane, Origin origin,
+                                                 uint32_t tempty_cluster0) {
+  const int ew = warp - 4, quarter = warp & 3, half = ew >> 2;
+  const int row = quarter * 32 + lane;
+  const int nchunks = p.NT >> 4, ngroups = (p.NT + 63) >> 6;
+  const int epi = EPI < 0 ? p.epi : EPI;
+  const bool has_res = epi != VMGB_EPI_STORE;          // host: bf16 residual, 16-byte aligned rows, NT <= 128 (one group per warp)
+  const uint32_t buf = smem_u32(bias_s) + 1024 + (uint32_t)ew * 4096u;
+  const int bw_shift = 31 - __clz(p.BW), bw_mask = p.BW - 1;
+  const int crow0 = lane >> 3, piece = lane & 7;
+  const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(p.res);
+  __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+  uint32_t acc_phase0 = 0, acc_phase1 = 0;
+  int it = 0, bias_combo = -1;
+
+  auto prefetch_res = [&](long long t, int grp) {
+    int combo, img, h0, w0; bool tvalid;
+    origin(t, combo, img, h0, w0, tvalid);
+    const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+    const int col = grp * 64 + piece * 8;
+    const bool cok = tvalid && col < p.NT && nt * p.NT + col + 8 <= p.Cout_g;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = crow0 + 4 * i, rr = quarter * 32 + r;
+      const int hh = h0 + (rr >> bw_shift), ww = w0 + (rr & bw_mask);
+      if (cok && hh < p.H && ww < p.W) {
+        const long long pix = ((long long)img * p.H + hh) * p.W + ww;
+        const __nv_bfloat16* rp = resp + pix * p.res_pitch + g * p.Cout_g + nt * p.NT + col;
+        const uint32_t dst = buf + (uint32_t)r * 128u + (uint32_t)((piece ^ (r & 7)) << 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rp) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if (has_res && half < ngroups && first < total) prefetch_res(first, half);
+  for (long long t = first; t < total; t += step, ++it) {
+    const int as = it & 1;
+    int combo, img, h0, w0; bool tvalid;
+    origin(t, combo, img, h0, w0, tvalid);
+    const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+    const int hh = h0 + (row >> bw_shift), ww = w0 + (row & bw_mask);
+    const bool pvalid = tvalid && hh < p.H && ww < p.W;
+    const long long pix = ((long long)img * p.H + hh) * p.W + ww;
+    const uint32_t aph = as ? acc_phase1 : acc_phase0;
+    if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_STRIDE;
+    if (combo != bias_combo) {                                            // bias of this (group, N tile) -> smem
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int c = ew * 32 + lane; c < p.NT; c += 256) {
+        const int nb = nt * p.NT + c;
+        bias_s[c] = (p.bias && nb < p.Cout_g) ? __ldg(p.bias + g * p.Cout_g + nb) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      bias_combo = combo;
+    }
+    if (has_res) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); }     // this item's residual group has landed
+    mbar_wait(tfull0 + 8 * as, aph);
+    tc_fence_after();
+    if (p.dbg & 2) {
+      tc_fence_before();
+      if (tempty_cluster0) mbar_arrive_cluster(tempty_cluster0 + 8 * as); else mbar_arrive(tempty0 + 8 * as);
+      continue;
+    }
+    const uint32_t rowbase = buf + (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    for (int grp = half; grp < ngroups; grp += 2) {
+      const int ch0 = grp * 4, chn = min(4, nchunks - ch0);
+      auto process = [&](int c, const uint32_t* raw) {
+        const uint32_t c0 = rowbase + (((uint32_t)(2 * c) ^ sw) << 4), c1 = rowbase + (((uint32_t)(2 * c + 1) ^ sw) << 4);
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+        const bool hp = has_res && pvalid && nt * p.NT + (ch0 + c) * 16 + 16 <= p.Cout_g;
+        if (hp) {
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(c0) : "memory");
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(c1) : "memory");
+        }
+        epilogue_chunk<ACT, EPI, 0>(p, raw, pvalid, img, hh, ww, pix, g, nt, ch0 + c, bias_s, hp, r0, r1, c0, c1);
+      };
+      uint32_t rawA[16], rawB[16];
+      __syncwarp();
+      tmem_ld16_issue(taddr + ch0 * 16, rawA);
+#pragma unroll 1
+      for (int c = 0; c < chn; c += 2) {
+        tmem_ld_wait();
+        __syncwarp();
+        if (c + 1 < chn) tmem_ld16_issue(taddr + (ch0 + c + 1) * 16, rawB);
+        process(c, rawA);
+        if (c + 1 >= chn) break;
+        tmem_ld_wait();
+        __syncwarp();
+        if (c + 2 < chn) tmem_ld16_issue(taddr + (ch0 + c + 2) * 16, rawA);
+        process(c + 1, rawB);
+      }
+      if (grp + 2 >= ngroups) {           // last TMEM read of this item: hand the accumulator back before the copy-out
+        tc_fence_before();
+        if (tempty_cluster0) mbar_arrive_cluster(tempty_cluster0 + 8 * as); else mbar_arrive(tempty0 + 8 * as);
+      }
+      __syncwarp();
+      // coalesced copy-out of the group: 4 rows x 128 contiguous bytes per warp instruction
+      const int col = grp * 64 + piece * 8;
+      const bool cok = tvalid && col < p.NT && nt * p.NT + col + 8 <= p.Cout_g && !(p.dbg & 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = crow0 + 4 * i, rr = quarter * 32 + r;
+        const int h2 = h0 + (rr >> bw_shift), w2 = w0 + (rr & bw_mask);
+        if (cok && h2 < p.H && w2 < p.W) {
+          uint4 val;
+          const uint32_t src = buf + (uint32_t)r * 128u + (uint32_t)((piece ^ (r & 7)) << 4);
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(src) : "memory");
+          const long long o = (((long long)img * p.H + h2) * p.W + w2) * p.out_pitch + g * p.Cout_g + nt * p.NT + col;
+          *reinterpret_cast<uint4*>(outp + o) = val;
+        }
+      }
+      __syncwarp();                       // buffer free: next group / next item's residual
+    }
+    if (half >= ngroups) {                // idle column half (NT <= 64): still a party of the accumulator hand-back
+      tc_fence_before();
+      if (tempty_cluster0) mbar_arrive_cluster(tempty_cluster0 + 8 * as); else mbar_arrive(tempty0 + 8 * as);
+    }
+    if (has_res && half < ngroups && t + step < total) prefetch_res(t + step, half);
+  }
+}
+
+template <class Origin>
+__device__ __forceinline__ void run_epilogue_w(const TcP& p, float* bias_s, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                               long long first, long long step, long long total, int warp, int lane, Origin origin,
+                                               uint32_t tempty_cluster0 = 0) {
+#define VMGB_EPIW_CASE(A, E)                                                                                             \
+  if (p.act == (A) && p.epi == (E)) {                                                                                    \
+    run_epilogue_w_t<A, E>(p, bias_s, tmem_base, tfull0, tempty0, first, step, total, warp, lane, origin, tempty_cluster0); \
+    return;                                                                                                              \
+  }
+  VMGB_EPIW_CASE(VMGB_ACT_NONE, VMGB_EPI_RESADD)
+  VMGB_EPIW_CASE(VMGB_ACT_RELU, VMGB_EPI_STORE)
+  VMGB_EPIW_CASE(VMGB_ACT_LRELU, VMGB_EPI_STORE)
+  VMGB_EPIW_CASE(VMGB_ACT_GELU, VMGB_EPI_STORE)
+  VMGB_EPIW_CASE(VMGB_ACT_NONE, VMGB_EPI_STORE)
+#undef VMGB_EPIW_CASE
+  run_epilogue_w_t<-1, -1>(p, bias_s, tmem_base, tfull0, tempty0, first, step, total, warp, lane, origin, tempty_cluster0);
 }
 
 constexpr int TC_THREADS = 384;      // warps 0-3: producer / MMA / TMEM alloc / spare ; warps 4-11: epilogue
@@ -633,6 +810,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
+    if (p.wst)
+      run_epilogue_w(p, bias_s, tmem_base, tfull0, tempty0, (long long)blockIdx.x, (long long)gridDim.x, p.total_tiles, warp, lane,
+                     [&](long long tile, int& combo, int& img, int& h0, int& w0, bool& valid) {
+                       combo = (int)(tile % ncombo);
+                       const long long mt = tile / ncombo;
+                       img = (int)(mt / tiles_per_img);
+                       const int rem = (int)(mt % tiles_per_img);
+                       h0 = (rem / p.tiles_w) * p.BH; w0 = (rem % p.tiles_w) * p.BW;
+                       valid = true;
+                     });
+    else
     run_epilogue(p, bias_s, tmem_base, tfull0, tempty0, (long long)blockIdx.x, (long long)gridDim.x, p.total_tiles, warp, lane,
                  [&](long long tile, int row, int& combo, int& img, int& hh, int& ww, bool& pvalid) {
                    combo = (int)(tile % ncombo);
@@ -655,199 +843,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
 
 // ---------------------------------------------------------------------------------------------
-// 3x3 convolution, traffic-reduced variant.  The per-tap kernel above re-reads the activation tile 9x
-// from L2; on B200 that (not the tensor pipe) bounds a 3x3 conv with C ~ 112..144.  Here a tile is
-// 16 rows x (8*nsub) columns of one image and the activation operand is loaded as "A units":
-//     unit (src, kb, s) = one TMA box {64 ch, 8*nsub cols, 18 rows} starting at column w0+s-1, row h0-1
-// One unit serves the three taps (r = 0,1,2 ; same column shift s) of both sub-tiles: the 128 rows of
-// the MMA for tap row r / sub-tile u start at byte (r*8*nsub + 8u)*128 of the unit -- a multiple of 1024,
-// so the canonical SWIZZLE_128B K-major descriptor applies with SBO = 8*nsub*128.  Activation L2 traffic
-// drops from 9x to 3 * 18/16 = 3.4x, and with nsub = 2 each weight box feeds two MMAs (M = 256 per CTA).
-// Rings: `ra` A units, `rb` weight boxes; accumulators: 2 (double buffer) x nsub x NT TMEM columns.
-// ---------------------------------------------------------------------------------------------
-template <bool kCluster>
-__global__ void __launch_bounds__(256, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB, const TcP p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_base = smem_base;
-  const uint32_t b_base = a_base + p.ra * p.a_unit_bytes;
-  const uint32_t bar_base = b_base + p.rb * p.b_stage_bytes;
-  const uint32_t afull0 = bar_base, aempty0 = afull0 + 8 * p.ra;
-  const uint32_t bfull0 = aempty0 + 8 * p.ra, bempty0 = bfull0 + 8 * p.rb;
-  const uint32_t tfull0 = bempty0 + 8 * p.rb, tempty0 = tfull0 + 16;
-  const uint32_t tmem_slot = tempty0 + 16;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    for (int i = 0; i < p.ra; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
-    for (int i = 0; i < p.rb; ++i) { mbar_init(bfull0 + 8 * i, 1); mbar_init(bempty0 + 8 * i, kCluster ? 2 : 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (kCluster) cluster_sync_all();        // peer barriers are initialised before anything is multicast into them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  const int tiles_per_img = p.tiles_h * p.tiles_w;
-  const int ncombo = p.groups * p.nt_per_g;
-  const int tw_cols = 8 * p.nsub;
-  // Work units.  Plain: unit = tile.  Cluster of 2: unit = (pair of consecutive M tiles, combo); CTA rank c takes
-  // M tile 2*pair + c (a missing odd tile becomes an all-out-of-bounds dummy so both CTAs stay in lockstep for
-  // the multicast weight ring).
-  const uint32_t crank = kCluster ? cluster_ctarank() : 0u;
-  const long long unit0 = kCluster ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
-  const long long unit_step = kCluster ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
-  const long long n_mt = (long long)p.n_img * tiles_per_img;
-  const long long n_units = kCluster ? ((n_mt + 1) / 2) * ncombo : p.total_tiles;
-
-  if (warp == 0) {
-    // ===================== TMA producer (whole warp runs the loops, one elected lane issues) =====================
-    int ia = 0, ib = 0; uint32_t pa = 0, pb = 0;
-    const uint32_t a_bytes = 18 * tw_cols * 128, b_bytes = p.NT * 128;
-    for (long long unit = unit0; unit < n_units; unit += unit_step) {
-      const int combo = (int)(unit % ncombo);
-      const long long mt = kCluster ? 2 * (unit / ncombo) + crank : unit / ncombo;
-      const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
-      const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);     // img == n_img for a dummy tile
-      const int h0 = (rem / p.tiles_w) * 16, w0 = (rem % p.tiles_w) * tw_cols;
-      for (int src = 0; src < p.n_src; ++src) {
-        const CUtensorMap* mA = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
-        for (int kb = 0; kb < p.kb_per_src; ++kb) {
-          const int ca = (p.n_src > 1 ? 0 : ((g * p.Cin_g) & ~7)) + kb * 64;
-          for (int sft = 0; sft < 3; ++sft) {
-            mbar_wait(aempty0 + 8 * ia, pa ^ 1);
-            if (elect_one()) {
-              mbar_expect_tx(afull0 + 8 * ia, a_bytes);
-              tma_load_4d(a_base + ia * p.a_unit_bytes, mA, afull0 + 8 * ia, ca, w0 + sft - 1, h0 - 1, img);
-            }
-            __syncwarp();
-            if (++ia == p.ra) { ia = 0; pa ^= 1; }
-            for (int r = 0; r < 3; ++r) {
-              const int brow = (g * 9 + r * 3 + sft) * p.Cout_g + nt * p.NT;
-              mbar_wait(bempty0 + 8 * ib, pb ^ 1);
-              if (elect_one()) {
-                mbar_expect_tx(bfull0 + 8 * ib, b_bytes);
-                if (kCluster)      // each CTA fetches half of the weight box and multicasts it to both
-                  tma_load_2d_mc(b_base + ib * p.b_stage_bytes + crank * (p.NT / 2) * 128, &mapB, bfull0 + 8 * ib, src * p.Cs + kb * 64,
-                                 brow + (int)crank * (p.NT / 2), (uint16_t)3);
-                else
-                  tma_load_2d(b_base + ib * p.b_stage_bytes, &mapB, bfull0 + 8 * ib, src * p.Cs + kb * 64, brow);
-              }
-              __syncwarp();
-              if (++ib == p.rb) { ib = 0; pb ^= 1; }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp runs the loops, one elected lane issues) =====================
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int ia = 0, ib = 0; uint32_t pa = 0, pb = 0;
-    uint32_t acc_phase0 = 0, acc_phase1 = 0;
-    int it = 0;
-    for (long long unit = unit0; unit < n_units; unit += unit_step, ++it) {
-      const int as = it & 1;
-      const uint32_t aph = as ? acc_phase1 : acc_phase0;
-      mbar_wait(tempty0 + 8 * as, aph ^ 1);
-      if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
-      const int g_mma = (int)(unit % ncombo) / p.nt_per_g;
-      const int kext = p.Cs + (p.n_src > 1 ? 0 : ((g_mma * p.Cin_g) & 7));
-      uint32_t accumulate = 0;
-      for (int src = 0; src < p.n_src; ++src) {
-        for (int kb = 0; kb < p.kb_per_src; ++kb) {
-          const int nks = min(4, (kext - kb * 64 + 15) >> 4);
-          for (int sft = 0; sft < 3; ++sft) {
-            mbar_wait(afull0 + 8 * ia, pa);
-            tc_fence_after();
-            const uint32_t a_unit = a_base + ia * p.a_unit_bytes;
-            for (int r = 0; r < 3; ++r) {
-              mbar_wait(bfull0 + 8 * ib, pb);
-              tc_fence_after();
-              const uint64_t bd = smem_desc_sw128(b_base + ib * p.b_stage_bytes);
-              if (elect_one()) {
-                for (int u = 0; u < p.nsub; ++u) {
-                  const uint64_t ad = smem_desc_sw128_sbo(a_unit + (uint32_t)(r * tw_cols + 8 * u) * 128u, (uint32_t)p.a_sbo);
-                  for (int ks = 0; ks < nks; ++ks)      // the very first K step of a sub-tile overwrites, all others accumulate
-                    umma_f16(d_tmem + u * p.NT, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)(ks > 0));
-                }
-                if (kCluster) umma_commit_mc(bempty0 + 8 * ib, (uint16_t)3); else umma_commit(bempty0 + 8 * ib);
-                if (r == 2) umma_commit(aempty0 + 8 * ia);
-              }
-              __syncwarp();
-              accumulate = 1;
-              if (++ib == p.rb) { ib = 0; pb ^= 1; }
-            }
-            if (++ia == p.ra) { ia = 0; pa ^= 1; }
-          }
-        }
-      }
-      if (elect_one()) umma_commit(tfull0 + 8 * as);
-      __syncwarp();
-    }
-  } else if (warp >= 4) {
-    // ===================== epilogue (4 warps) =====================
-    const int ew = warp - 4, quarter = warp & 3;
-    const int row = quarter * 32 + lane;             // MMA row = dy*8 + dx of the sub-tile
-    uint32_t acc_phase0 = 0, acc_phase1 = 0;
-    int it = 0, bias_combo = -1;
-    float* bias_s = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
-    for (long long unit = unit0; unit < n_units; unit += unit_step, ++it) {
-      const int as = it & 1;
-      const int combo = (int)(unit % ncombo);
-      const long long mt = kCluster ? 2 * (unit / ncombo) + crank : unit / ncombo;
-      const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
-      const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
-      const int hh = (rem / p.tiles_w) * 16 + (row >> 3);
-      const uint32_t aph = as ? acc_phase1 : acc_phase0;
-      if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
-      for (int u = 0; u < p.nsub; ++u) {
-        const int ww = (rem % p.tiles_w) * tw_cols + 8 * u + (row & 7);
-        const bool pvalid = hh < p.H && ww < p.W && img < p.n_img;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_STRIDE + u * p.NT;
-        epilogue_tile<4>(p, bias_s, bias_combo, combo, ew, lane, taddr, img, hh, ww, pvalid, g, nt, tfull0 + 8 * as, aph, u == 0);
-      }
-      tc_fence_before();
-      mbar_arrive(tempty0 + 8 * as);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (kCluster) cluster_sync_all();        // nobody exits while the peer can still multicast into / arrive on this CTA
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------------
 // RxR (3x3 / 7x7) convolution, WEIGHT-STATIONARY variant (the trajectory resblock convs: 63-67 % of all FLOPs; SPyNet).
 // Measured on B200: the per-tap kernel is bound by the L2 -> SM fabric (~9 TB/s aggregate, ~60 GB/s per SM),
 // moving 484 KB per 128-pixel tile at C = N = 112, of which 226 KB are the same weights again and again.
 // Here the output channels of a group are split into `nt_per_g` slices of NT columns and every CTA keeps the
 // COMPLETE weight set of one slice (9 taps x K blocks, <= ~150 KB) resident in shared memory for the whole
-// launch; only activations stream, as column-shifted 18-row "A units" (see conv3x3_tc_kernel): one TMA box
+// launch; only activations stream, as column-shifted (16+R-1)-row "A units": one TMA box
 // {64 ch, 8 cols, 18 rows} per (K block, column shift) serves the three taps of that shift.  Per tile and
 // slice the fabric moves ~97 KB instead of 484 KB.
 // Work split: CTA b owns combo = b % (groups*slices) for the whole launch and walks the M tiles
 // b / ncombo, b / ncombo + grid / ncombo, ...
 // ---------------------------------------------------------------------------------------------
-template <int RR>      // square odd kernel size: 3 or 7 (compile-time so that the MMA issue loop stays tight)
+// BWX = 8: one box {64 ch, 8 cols, 16+R-1 rows} per column shift (R loads per K block, row shifts are +1024 B
+// descriptor offsets).  BWX > 8 ("wide"): ONE box {64 ch, BWX >= 8+R-1 cols, 16+R-1 rows} per K block; a tap
+// (r, s) is the descriptor start (r*BWX + s)*128 B with 8-row groups BWX*128 B apart.  That start is not
+// 1024-byte aligned, which works because the 128B swizzle is a function of the shared-memory ADDRESS bits
+// (TMA writes and tcgen05 reads agree as long as the unit base is 1024-aligned) - R x less activation traffic.
+template <int RR, int BWX>      // square odd kernel size: 3 or 7 (compile-time so that the MMA issue loop stays tight)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_ws_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB, const TcP p) {
@@ -902,7 +914,8 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
     __syncwarp();
     int ia = 0; uint32_t pa = 0;
-    const uint32_t a_bytes = (uint32_t)UROWS * 8 * 128;
+    constexpr uint32_t a_bytes = (uint32_t)UROWS * BWX * 128;
+    constexpr int NSFT = BWX == 8 ? RR : 1;
     for (long long mt = first; mt < n_mt; mt += step) {
       const int img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
       const int h0 = (rem / p.tiles_w) * 16, w0 = (rem % p.tiles_w) * 8;
@@ -910,7 +923,7 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const CUtensorMap* mA = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
         for (int kb = 0; kb < p.kb_per_src; ++kb) {
           const int ca = (p.n_src > 1 ? 0 : ((g * p.Cin_g) & ~7)) + kb * 64;
-          for (int sft = 0; sft < RR; ++sft) {
+          for (int sft = 0; sft < NSFT; ++sft) {
             mbar_wait(aempty0 + 8 * ia, pa ^ 1);
             if (elect_one()) {
               mbar_expect_tx(afull0 + 8 * ia, a_bytes);
@@ -943,19 +956,42 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         for (int kb = 0; kb < p.kb_per_src; ++kb) {
           const int nks = min(4, (kext - kb * 64 + 15) >> 4);
           const bool last_kb = src == p.n_src - 1 && kb == p.kb_per_src - 1;
-          for (int sft = 0; sft < RR; ++sft) {
+          if (BWX == 8) {
+            for (int sft = 0; sft < RR; ++sft) {
+              mbar_wait(afull0 + 8 * ia, pa);
+              tc_fence_after();
+              const uint32_t a_unit = a_base + ia * p.a_unit_bytes;
+              if (elect_one()) {
+                for (int r = 0; r < RR; ++r) {
+                  const uint64_t ad = smem_desc_sw128(a_unit + (uint32_t)r * 1024u);
+                  const uint64_t bd = smem_desc_sw128(w_base + ((src * p.kb_per_src + kb) * TAPS + r * RR + sft) * p.b_stage_bytes);
+                  for (int ks = 0; ks < nks; ++ks)
+                    umma_f16(d_tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)((r | ks) > 0));
+                }
+                umma_commit(aempty0 + 8 * ia);
+                if (last_kb && sft == RR - 1) umma_commit(tfull0 + 8 * as);
+              }
+              __syncwarp();
+              accumulate = 1;
+              if (++ia == p.ra) { ia = 0; pa ^= 1; }
+            }
+          } else {
             mbar_wait(afull0 + 8 * ia, pa);
             tc_fence_after();
             const uint32_t a_unit = a_base + ia * p.a_unit_bytes;
             if (elect_one()) {
               for (int r = 0; r < RR; ++r) {
-                const uint64_t ad = smem_desc_sw128(a_unit + (uint32_t)r * 1024u);
-                const uint64_t bd = smem_desc_sw128(w_base + ((src * p.kb_per_src + kb) * TAPS + r * RR + sft) * p.b_stage_bytes);
-                for (int ks = 0; ks < nks; ++ks)
-                  umma_f16(d_tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)((r | ks) > 0));
+                for (int sft = 0; sft < RR; ++sft) {
+                  const uint32_t a_addr = a_unit + (uint32_t)(r * BWX + sft) * 128u;
+                  uint64_t ad = smem_desc_sw128_sbo(a_addr, (uint32_t)BWX * 128u);
+                  if (p.rb) ad |= (uint64_t)((a_addr >> 7) & 7u) << 49;      // experiment: matrix base offset field
+                  const uint64_t bd = smem_desc_sw128(w_base + ((src * p.kb_per_src + kb) * TAPS + r * RR + sft) * p.b_stage_bytes);
+                  for (int ks = 0; ks < nks; ++ks)
+                    umma_f16(d_tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)((r | sft | ks) > 0));
+                }
               }
               umma_commit(aempty0 + 8 * ia);
-              if (last_kb && sft == RR - 1) umma_commit(tfull0 + 8 * as);
+              if (last_kb) umma_commit(tfull0 + 8 * as);
             }
             __syncwarp();
             accumulate = 1;
@@ -966,6 +1002,16 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
+    if (p.wst)
+      run_epilogue_w(p, bias_s, tmem_base, tfull0, tempty0, first, step, n_mt, warp, lane,
+                     [&](long long mt, int& cmb, int& img, int& h0, int& w0, bool& valid) {
+                       cmb = combo;
+                       img = (int)(mt / tiles_per_img);
+                       const int rem = (int)(mt % tiles_per_img);
+                       h0 = (rem / p.tiles_w) * 16; w0 = (rem % p.tiles_w) * 8;
+                       valid = true;
+                     });
+    else
     run_epilogue(p, bias_s, tmem_base, tfull0, tempty0, first, step, n_mt, warp, lane,
                  [&](long long mt, int row, int& cmb, int& img, int& hh, int& ww, bool& pvalid) {
                    cmb = combo;
@@ -985,6 +1031,174 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 convolution, weight-stationary on a CTA PAIR (tcgen05 cta_group::2, M = 256).
+// The single-CTA weight-stationary kernel above cannot hold the 9 x K x 112 weights of a trajectory resblock
+// conv (258 KB) and therefore splits the output channels in two slices: every activation unit crosses the
+// L2 -> SM fabric twice and the MMAs run at N = 64, where operand reads from shared memory (A: 4 KB + B: 2 KB
+// per 128x64x16 instruction) cost more cycles than the math.  A CTA pair fixes both: each CTA keeps only its
+// HALF of the weight rows (N/2 x 9 x K, 129 KB at C = 112), loads the wide activation unit of its OWN 16x8
+// tile once, and the leader's single thread issues 256 x N x 16 MMAs that read A from both SMs and half of B
+// from each.  Barriers: activation / weight TMA of both CTAs complete on the LEADER's full barriers
+// (cta_group::2 TMA form), tcgen05.commit multicasts "slot free" and "accumulator full" to both CTAs, and the
+// 2 x 256 epilogue threads of the pair arrive on the leader's "accumulator empty" barrier.
+// Work split: cluster c owns combo = c % slices and walks the tile PAIRS c / slices, + clusters / slices, ...
+// (tile 2t -> rank 0, tile 2t+1 -> rank 1; an odd tail tile is loaded fully out of bounds = zeros).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcP p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr int RR = 3, BWX = 10, TAPS = 9, UROWS = 18;
+  // weights: one SWIZZLE_128B box {64 k, N/2 rows} per (K block, tap).  (A dense SWIZZLE_32B layout, one {16 k, N/2}
+  // box per K = 16 slice, saves 16 KB at C = 112 but measured ~25 % slower MMA issue on B200.)
+  const int nboxes = p.kb_per_src * TAPS;
+  const uint32_t a_base = smem_base;
+  const uint32_t w_base = a_base + p.ra * p.a_unit_bytes;
+  const uint32_t bar_base = (w_base + nboxes * p.b_stage_bytes + 1023u) & ~1023u;
+  const uint32_t afull0 = bar_base, aempty0 = afull0 + 8 * p.ra;
+  const uint32_t wfull = aempty0 + 8 * p.ra;
+  const uint32_t tfull0 = wfull + 16, tempty0 = tfull0 + 16;
+  const uint32_t tmem_slot = tempty0 + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.ra; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
+    mbar_init(wfull, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 512); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();            // barriers of both CTAs initialised before any remote complete_tx / arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
+
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int ncombo = p.nt_per_g;                      // groups == 1
+  const long long cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int combo = (int)(cl % ncombo);
+  const int nt = combo;
+  const long long first = cl / ncombo, step = ncl / ncombo;
+  const long long n_mt = (long long)p.n_img * tiles_per_img;
+  const long long n_pairs = (n_mt + 1) >> 1;
+  const int NH = p.NT >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    const uint32_t wfull_l = mapa_rank(wfull, 0), afull0_l = mapa_rank(afull0, 0);
+    if (elect_one()) {                 // this CTA's half of the weight slice, once
+      if (rank == 0) mbar_expect_tx(wfull, (uint32_t)(2 * nboxes * NH * 128));
+      for (int kb = 0; kb < p.kb_per_src; ++kb)
+        for (int tap = 0; tap < TAPS; ++tap)
+          tma_load_2d_2sm(w_base + (kb * TAPS + tap) * p.b_stage_bytes, &mapB, wfull_l, kb * 64, tap * p.Cout_g + nt * p.NT + (int)rank * NH);
+    }
+    __syncwarp();
+    int ia = 0; uint32_t pa = 0;
+    constexpr uint32_t a_bytes = (uint32_t)UROWS * BWX * 128;
+    for (long long t = first; t < n_pairs; t += step) {
+      const long long mt = 2 * t + rank;
+      int img = p.n_img, h0 = 0, w0 = 0;             // odd tail: a box entirely outside the tensor (zero fill)
+      if (mt < n_mt) {
+        img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
+        h0 = (rem / p.tiles_w) * 16; w0 = (rem % p.tiles_w) * 8;
+      }
+      for (int kb = 0; kb < p.kb_per_src; ++kb) {
+        mbar_wait(aempty0 + 8 * ia, pa ^ 1);
+        if (elect_one()) {
+          if (p.dbg & 4) { if (rank == 0) mbar_arrive(afull0 + 8 * ia); }
+          else {
+            if (rank == 0) mbar_expect_tx(afull0 + 8 * ia, 2 * a_bytes);
+            tma_load_4d_2sm(a_base + ia * p.a_unit_bytes, &mapA, afull0_l + 8 * ia, kb * 64, w0 - 1, h0 - 1, img);
+          }
+        }
+        __syncwarp();
+        if (++ia == p.ra) { ia = 0; pa ^= 1; }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    int ia = 0; uint32_t pa = 0;
+    uint32_t acc_phase0 = 0, acc_phase1 = 0;
+    int it = 0;
+    const uint32_t issue = elect_one() ? 1u : 0u;        // one fixed lane issues every tcgen05 instruction of this warp
+    mbar_wait(wfull, 0);
+    tc_fence_after();
+    for (long long t = first; t < n_pairs; t += step, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = as ? acc_phase1 : acc_phase0;
+      mbar_wait(tempty0 + 8 * as, aph ^ 1);
+      if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < p.kb_per_src; ++kb) {
+        const int nks = min(4, (p.Cs - kb * 64 + 15) >> 4);
+        mbar_wait(afull0 + 8 * ia, pa);
+        tc_fence_after();
+        const uint32_t a_unit = a_base + ia * p.a_unit_bytes;
+        if (!(p.dbg & 1)) {
+#pragma unroll
+          for (int tap = 0; tap < TAPS; ++tap) {
+            const uint64_t ad = smem_desc_sw128_sbo(a_unit + (uint32_t)((tap / RR) * BWX + (tap % RR)) * 128u, (uint32_t)BWX * 128u);
+            const uint64_t bd = smem_desc_sw128(w_base + (kb * TAPS + tap) * p.b_stage_bytes);
+            for (int ks = 0; ks < nks; ++ks)
+              umma_f16_2sm_if(issue, d_tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)((tap | ks) > 0));
+          }
+        }
+        umma_commit_2sm_if(issue, aempty0 + 8 * ia, (uint16_t)3);
+        if (kb == p.kb_per_src - 1) umma_commit_2sm_if(issue, tfull0 + 8 * as, (uint16_t)3);
+        __syncwarp();
+        accumulate = 1;
+        if (++ia == p.ra) { ia = 0; pa ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps per CTA, each CTA drains its own 128 accumulator rows) =====================
+    if (p.wst)
+      run_epilogue_w(p, bias_s, tmem_base, tfull0, tempty0, first, step, n_pairs, warp, lane,
+                     [&](long long t, int& cmb, int& img, int& h0, int& w0, bool& valid) {
+                       const long long mt = 2 * t + rank;
+                       cmb = combo;
+                       valid = mt < n_mt;
+                       img = valid ? (int)(mt / tiles_per_img) : 0;
+                       const int rem = valid ? (int)(mt % tiles_per_img) : 0;
+                       h0 = (rem / p.tiles_w) * 16; w0 = (rem % p.tiles_w) * 8;
+                     },
+                     mapa_rank(tempty0, 0));
+    else
+    run_epilogue(p, bias_s, tmem_base, tfull0, tempty0, first, step, n_pairs, warp, lane,
+                 [&](long long t, int row, int& cmb, int& img, int& hh, int& ww, bool& pvalid) {
+                   const long long mt = 2 * t + rank;
+                   cmb = combo;
+                   img = (int)(mt / tiles_per_img);
+                   const int rem = (int)(mt % tiles_per_img);
+                   hh = (rem / p.tiles_w) * 16 + (row >> 3);
+                   ww = (rem % p.tiles_w) * 8 + (row & 7);
+                   pvalid = mt < n_mt && hh < p.H && ww < p.W;
+                   if (mt >= n_mt) { img = 0; hh = 0; ww = 0; }
+                 },
+                 mapa_rank(tempty0, 0));
+  }
+
+  tc_fence_before();
+  cluster_sync_all();            // nobody exits (or frees TMEM) while the peer can still read this CTA's smem / signal its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -995,32 +1209,45 @@ static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 0;
 static int g_smem_optin = 0;
 static std::once_flag g_once;
+static int g_no_wst = 0;      // VMGB_NO_WST=1: A/B switch (tools/microbench.py) for the warp-private staging epilogue
 
 static void tc_init() {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
     g_encode = (EncodeTiledFn)fn;
+  if (const char* e = getenv("VMGB_NO_WST")) g_no_wst = atoi(e);      // A/B switch for tools/microbench.py
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (g_smem_optin > 0) {
     cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-    cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-    cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-    cudaFuncSetAttribute(conv3x3_ws_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-    cudaFuncSetAttribute(conv3x3_ws_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+    cudaFuncSetAttribute(conv3x3_ws_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+    cudaFuncSetAttribute(conv3x3_ws_kernel<7, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+    cudaFuncSetAttribute(conv3x3_ws_kernel<3, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+    cudaFuncSetAttribute(conv3x3_ws_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+    cudaFuncSetAttribute(conv3x3_ws2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
   }
 }
 
 static bool encode_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                        const cuuint32_t* box) {
+                        const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+constexpr int WST_BYTES = 8 * 4096;     // run_epilogue_w: one 32-row x 64-column bf16 buffer per epilogue warp
+
+// whether the warp-private transposition epilogue applies (see run_epilogue_w_t)
+static bool wst_ok(int NT, int Cout_g, const void* out, int out_dt, int out_pitch, int ps, int epi, const void* res, int res_dt, int res_pitch) {
+  if (g_no_wst) return false;
+  if (out_dt != VMGB_BF16 || ps != 0 || (out_pitch & 7) || (Cout_g & 7) || (reinterpret_cast<uintptr_t>(out) & 15)) return false;
+  if (epi == VMGB_EPI_STORE) return true;
+  return epi == VMGB_EPI_RESADD && res_dt == VMGB_BF16 && !(res_pitch & 7) && !(reinterpret_cast<uintptr_t>(res) & 15) && NT <= 128;
 }
 
 }  // namespace vmgb
@@ -1060,37 +1287,105 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   p.bias = (const float*)bias; p.out = out; p.res = res; p.aux = aux;
   p.out_dt = out_dt; p.out_pitch = out_pitch; p.res_dt = res_dt; p.res_pitch = res_pitch; p.aux_dt = aux_dt; p.aux_pitch = aux_pitch;
   p.act = act; p.alpha = act_alpha; p.out_scale = out_scale; p.epi = epi; p.res_scale = res_scale; p.ps = pixel_shuffle;
+  p.dbg = 0; p.wst = 0;
   p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0; p.res_smem = 0; p.out_smem = 0; p.aux_smem = 0;
   const int budget = g_smem_optin - 1024 - 512 - 1024;     // alignment slack, barriers, bias staging
 
-  // ---- weight-stationary 3x3 kernel (variant 8, or auto when the launch is large enough to amortise the
-  //      one-off weight load): find the smallest number of output-channel slices whose weights fit
-  if (R == S && (R == 3 || R == 7) && H >= 8 && W >= 8 && (variant == 8 || variant == 0)) {
-    const int urows = 16 + R - 1, ubytes = urows * 8 * 128;
-    const int nboxes = n_src * p.kb_per_src * R * R;
+  // ---- CTA-pair weight-stationary 3x3 kernel (variant 13, or auto): single source, ungrouped
+  if (variant >= 32) { p.dbg = (variant >> 5) & 15; variant = 13; }      // probes: 13 + 32*dbg
+  if (R == 3 && S == 3 && H >= 8 && W >= 8 && n_src == 1 && groups == 1 && (variant == 0 || variant == 13)) {
+    const int ubytes = (18 * 10 * 128 + 1023) / 1024 * 1024;
+    const int nboxes = 9 * p.kb_per_src;                  // SWIZZLE_128B weight boxes {64 k, NT/2 rows}
     const long long n_mt = (long long)n_img * ((H + 15) / 16) * ((W + 7) / 8);
-    int best_slices = 0, best_nt = 0, best_ra = 0, best_res = 0, best_out = 0;
+    const long long n_pairs = (n_mt + 1) / 2;
+    int best_slices = 0, best_nt = 0, best_ra = 0, best_res = 0, best_out = 0, best_wst = 0;
     for (int sl = 1; sl <= 8 && !best_slices; ++sl) {
       const int nts = (((Cout_g + sl - 1) / sl) + 15) / 16 * 16;
       if (nts > 256) continue;
-      const int resb = (epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0) ? nts * 256 : 0;
-      int left = budget - nboxes * nts * 128 - resb;
-      // coalesced copy-out for wide outputs (FFN hidden tensor): only if the activation ring keeps >= 3 units
+      const int wbytes = (nboxes * (nts / 2) * 128 + 1023) / 1024 * 1024;
+      const int old_resb = (epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0) ? nts * 256 : 0;
+      // the warp-private staging epilogue only where it does not cost an activation ring slot
+      const bool wst = wst_ok(nts, Cout_g, out, out_dt, out_pitch, pixel_shuffle, epi, res, res_dt, res_pitch) &&
+                       (budget - wbytes - WST_BYTES) / ubytes >= 3 && (budget - wbytes - WST_BYTES) / ubytes >= (budget - wbytes - old_resb) / ubytes;
+      const int resb = wst ? WST_BYTES : ((epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0) ? nts * 256 : 0);
+      int left = budget - wbytes - resb;
       int outb = 0;
-      if (Cout >= 256 && out_dt == VMGB_BF16 && pixel_shuffle == 0 && (out_pitch & 7) == 0 && (Cout_g & 7) == 0 &&
+      if (!wst && Cout >= 256 && out_dt == VMGB_BF16 && pixel_shuffle == 0 && (out_pitch & 7) == 0 && (Cout_g & 7) == 0 &&
           !(reinterpret_cast<uintptr_t>(out) & 15) && (left - 128 * (nts + 8) * 2) / ubytes >= 3)
         outb = 128 * (nts + 8) * 2;
       left -= outb;
       const int ra = left / ubytes;
-      if (ra >= 2) { best_slices = sl; best_nt = nts; best_ra = ra > 6 ? 6 : ra; best_res = resb; best_out = outb; }
+      if (ra >= 2) { best_slices = sl; best_nt = nts; best_ra = ra > 6 ? 6 : ra; best_res = resb; best_out = outb; best_wst = wst; }
+    }
+    const long long clusters_max = (g_num_sms / 2) / (best_slices ? best_slices : 1);
+    const bool worth = best_slices && clusters_max >= 1 && n_pairs >= 3 * clusters_max && p.kb_per_src <= 3;
+    if (best_slices && clusters_max >= 1 && (variant == 13 || worth)) {
+      if (reinterpret_cast<uintptr_t>(x) & 15) return VMGB_EINVAL;
+      p.nt_per_g = best_slices; p.NT = best_nt; p.b_stage_bytes = (best_nt / 2) * 128; p.ra = best_ra; p.out_smem = best_out;
+      p.wst = best_wst; p.res_smem = best_wst ? 0 : best_res;
+      p.BH = 16; p.BW = 8; p.a_unit_bytes = ubytes; p.stages = 0;
+      p.tiles_h = (H + 15) / 16; p.tiles_w = (W + 7) / 8;
+      p.total_tiles = n_mt * p.nt_per_g;
+      CUtensorMap mA, mB;
+      {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+        cuuint64_t str[3] = {(cuuint64_t)x_pitch * 2, (cuuint64_t)W * x_pitch * 2, (cuuint64_t)H * W * x_pitch * 2};
+        cuuint32_t box[4] = {64, 10, 18, 1};
+        if (!encode_bf16(&mA, x, 4, dims, str, box)) return VMGB_EINVAL;
+      }
+      {
+        cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)9 * Cout_g};
+        cuuint64_t str[1] = {(cuuint64_t)Kp * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)(p.NT / 2)};
+        if (!encode_bf16(&mB, w, 2, dims, str, box)) return VMGB_EINVAL;
+      }
+      long long per = n_pairs < clusters_max ? n_pairs : clusters_max;
+      const int smem = p.ra * p.a_unit_bytes + (nboxes * p.b_stage_bytes + 1023) / 1024 * 1024 + 1024 + 512 + 1024 + best_res + p.out_smem;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(2 * per * best_slices)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel, mA, mB, p);
+      if (e != cudaSuccess) { g_last_cuda_error = (int)e; return VMGB_ECUDA; }
+      return check_launch();
+    }
+  }
+  if (variant == 13) return VMGB_EUNSUPPORTED;
+
+  // ---- weight-stationary 3x3 kernel (variant 8, or auto when the launch is large enough to amortise the
+  //      one-off weight load): find the smallest number of output-channel slices whose weights fit
+  if (R == S && (R == 3 || R == 7) && H >= 8 && W >= 8 && (variant == 0 || (variant >= 8 && variant <= 12))) {
+    // variants 9..12 (experiments, 3x3 only): wide activation boxes, 9/10 = 10 columns, 11/12 = 16 columns; even = base-offset field set
+    const int bwx = (R == 3 && variant >= 9) ? (variant <= 10 ? 10 : 16) : 8;
+    const int urows = 16 + R - 1, ubytes = (urows * bwx * 128 + 1023) / 1024 * 1024;
+    const int nboxes = n_src * p.kb_per_src * R * R;
+    const long long n_mt = (long long)n_img * ((H + 15) / 16) * ((W + 7) / 8);
+    int best_slices = 0, best_nt = 0, best_ra = 0, best_res = 0, best_out = 0, best_wst = 0;
+    for (int sl = 1; sl <= 8 && !best_slices; ++sl) {
+      const int nts = (((Cout_g + sl - 1) / sl) + 15) / 16 * 16;
+      if (nts > 256) continue;
+      const bool wst = wst_ok(nts, Cout_g, out, out_dt, out_pitch, pixel_shuffle, epi, res, res_dt, res_pitch);
+      const int resb = wst ? WST_BYTES : ((epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0) ? nts * 256 : 0);
+      int left = budget - nboxes * nts * 128 - resb;
+      // coalesced copy-out for wide outputs (FFN hidden tensor): only if the activation ring keeps >= 3 units
+      int outb = 0;
+      if (!wst && Cout >= 256 && out_dt == VMGB_BF16 && pixel_shuffle == 0 && (out_pitch & 7) == 0 && (Cout_g & 7) == 0 &&
+          !(reinterpret_cast<uintptr_t>(out) & 15) && (left - 128 * (nts + 8) * 2) / ubytes >= 3)
+        outb = 128 * (nts + 8) * 2;
+      left -= outb;
+      const int ra = left / ubytes;
+      if (ra >= 2) { best_slices = sl; best_nt = nts; best_ra = ra > 6 ? 6 : ra; best_res = resb; best_out = outb; best_wst = wst; }
     }
     const long long ctas = g_num_sms / (groups * (best_slices ? best_slices : 1));
     // auto: measured wins (tools/microbench.py) are the single-source, ungrouped convs with <= 2 K blocks
     // (trajectory resblocks at C=112, recon head); at least ~4 M tiles per CTA amortise the resident weight load
     const bool worth = best_slices && ctas >= 1 && n_mt >= 4 * ctas && n_src == 1 && groups == 1 && p.kb_per_src <= 2 &&
                        (R == 3 || Cin <= 32);      // 7x7: measured wins only where the 64-wide K block is mostly padding
-    if (best_slices && ctas >= 1 && (variant == 8 || worth)) {
-      p.nt_per_g = best_slices; p.NT = best_nt; p.b_stage_bytes = best_nt * 128; p.ra = best_ra; p.res_smem = best_res; p.out_smem = best_out;
+    if (best_slices && ctas >= 1 && (variant >= 8 || worth)) {
+      p.rb = (variant == 10 || variant == 12) ? 1 : 0;
+      p.nt_per_g = best_slices; p.NT = best_nt; p.b_stage_bytes = best_nt * 128; p.ra = best_ra; p.out_smem = best_out;
+      p.wst = best_wst; p.res_smem = best_wst ? 0 : best_res;
       p.BH = 16; p.BW = 8; p.a_unit_bytes = ubytes; p.stages = 0;
       p.tiles_h = (H + 15) / 16; p.tiles_w = (W + 7) / 8;
       p.total_tiles = n_mt * groups * p.nt_per_g;
@@ -1102,7 +1397,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
         if (reinterpret_cast<uintptr_t>(ptr) & 15) return VMGB_EINVAL;
         cuuint64_t dims[4] = {(cuuint64_t)c_extent, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
         cuuint64_t str[3] = {(cuuint64_t)x_pitch * 2, (cuuint64_t)W * x_pitch * 2, (cuuint64_t)H * W * x_pitch * 2};
-        cuuint32_t box[4] = {64, 8, (cuuint32_t)urows, 1};
+        cuuint32_t box[4] = {64, (cuuint32_t)bwx, (cuuint32_t)urows, 1};
         if (!encode_bf16(&mA[s], ptr, 4, dims, str, box)) return VMGB_EINVAL;
       }
       {
@@ -1113,53 +1408,42 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       }
       const int ncombo = groups * p.nt_per_g;
       long long per = n_mt < ctas ? n_mt : ctas;
-      const int smem = p.ra * p.a_unit_bytes + nboxes * p.b_stage_bytes + 1024 + 512 + 1024 + p.res_smem + p.out_smem;
-      if (R == 3) conv3x3_ws_kernel<3><<<(unsigned)(per * ncombo), TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
-      else conv3x3_ws_kernel<7><<<(unsigned)(per * ncombo), TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
+      const int smem = p.ra * p.a_unit_bytes + nboxes * p.b_stage_bytes + 1024 + 512 + 1024 + best_res + p.out_smem;
+      const dim3 grid((unsigned)(per * ncombo));
+      if (R == 7) conv3x3_ws_kernel<7, 8><<<grid, TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
+      else if (bwx == 10) conv3x3_ws_kernel<3, 10><<<grid, TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
+      else if (bwx == 16) conv3x3_ws_kernel<3, 16><<<grid, TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
+      else conv3x3_ws_kernel<3, 8><<<grid, TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
       return check_launch();
     }
-    if (variant == 8) return VMGB_EUNSUPPORTED;
+    if (variant >= 8) return VMGB_EUNSUPPORTED;
   }
 
-  // variant: 0 = auto, 1 = force the per-tap kernel, 2 = 3x3 kernel with nsub = 1, 3 = 3x3 kernel with nsub = 2;
-  // +4 = 2-CTA cluster with multicast weight boxes (3x3 kernel only)
-  const bool cluster = (variant & 4) != 0;
-  variant &= 3;
-  const bool use3x3 = R == 3 && S == 3 && H >= 8 && W >= 8 && variant >= 2;     // explicit request only (see ops.py)
-  if (cluster && !use3x3) return VMGB_EINVAL;
-  if (use3x3) {
-    p.nsub = (variant == 2) ? 1 : ((2 * p.NT <= ACC_STRIDE && W > 8) ? 2 : 1);
-    if (variant == 3 && 2 * p.NT > ACC_STRIDE) return VMGB_EINVAL;
-    p.BH = 16; p.BW = 8 * p.nsub;
-    p.a_unit_bytes = 18 * p.BW * 128;            // multiple of 1024
-    p.a_sbo = p.BW * 128;
-    p.ra = 3;
-    p.rb = (budget - p.ra * p.a_unit_bytes) / p.b_stage_bytes;
-    if (p.rb > 8) p.rb = 8;
-    if (p.rb < 3) { p.ra = 2; p.rb = (budget - p.ra * p.a_unit_bytes) / p.b_stage_bytes; if (p.rb > 8) p.rb = 8; }
-    if (p.rb < 2) return VMGB_EUNSUPPORTED;
-    p.stages = 0;
+  // ---- per-tap kernel (variant 1, or auto for everything else)
+  if (variant != 0 && variant != 1) return VMGB_EINVAL;
+  if (H == 1) { p.BW = 128; p.BH = 1; }
+  else { p.BW = W >= 16 ? 16 : (W >= 8 ? 8 : 4); p.BH = 128 / p.BW; }
+  const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
+  p.res_smem = 0; p.out_smem = 0; p.aux_smem = 0;
+  int epi_smem = 0;
+  if (wst_ok(p.NT, Cout_g, out, out_dt, out_pitch, pixel_shuffle, epi, res, res_dt, res_pitch) && (budget - WST_BYTES) / stage_bytes >= 3) {
+    p.wst = 1; epi_smem = WST_BYTES;      // warp-private transposition staging: coalesced residual reads and output writes
   } else {
-    if (H == 1) { p.BW = 128; p.BH = 1; }
-    else { p.BW = W >= 16 ? 16 : (W >= 8 ? 8 : 4); p.BH = 128 / p.BW; }
-    const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
-    // residual staging (2 buffers of 128 rows x NT bf16) when it leaves at least 4 pipeline stages
-    p.res_smem = 0;
+    // residual staging (128 rows x NT bf16, one item ahead) when it leaves at least 4 pipeline stages
     if (epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0 && (budget - p.NT * 256) / stage_bytes >= 4)
       p.res_smem = p.NT * 256;
     // output staging (coalesced copy-out): bf16 output, 16-byte aligned channel runs, whole-vector validity
-    p.out_smem = 0;
     if (out_dt == VMGB_BF16 && pixel_shuffle == 0 && (out_pitch & 7) == 0 && (Cout_g & 7) == 0 && !(reinterpret_cast<uintptr_t>(out) & 15) &&
         (budget - p.res_smem - 128 * (p.NT + 8) * 2) / stage_bytes >= 4)
       p.out_smem = 128 * (p.NT + 8) * 2;
-    p.aux_smem = 0;
     if (epi == VMGB_EPI_GATE && p.res_smem && aux_dt == VMGB_BF16 && aux_pitch == res_pitch && !(reinterpret_cast<uintptr_t>(aux) & 15) &&
         (budget - p.res_smem - p.out_smem - p.NT * 256) / stage_bytes >= 3)
       p.aux_smem = p.NT * 256;
-    p.stages = (budget - p.res_smem - p.out_smem - p.aux_smem) / stage_bytes;
-    if (p.stages > 8) p.stages = 8;
-    if (p.stages < 2) return VMGB_EUNSUPPORTED;
+    epi_smem = p.res_smem + p.out_smem + p.aux_smem;
   }
+  p.stages = (budget - epi_smem) / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) return VMGB_EUNSUPPORTED;
   p.tiles_h = (H + p.BH - 1) / p.BH; p.tiles_w = (W + p.BW - 1) / p.BW;
   p.total_tiles = (long long)n_img * p.tiles_h * p.tiles_w * groups * p.nt_per_g;
 
@@ -1173,34 +1457,17 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
     if (reinterpret_cast<uintptr_t>(ptr) & 15) return VMGB_EINVAL;
     cuuint64_t dims[4] = {(cuuint64_t)c_extent, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
     cuuint64_t str[3] = {(cuuint64_t)x_pitch * 2, (cuuint64_t)W * x_pitch * 2, (cuuint64_t)H * W * x_pitch * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)p.BW, (cuuint32_t)(use3x3 ? 18 : p.BH), 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
     if (!encode_bf16(&mA[s], ptr, 4, dims, str, box)) return VMGB_EINVAL;
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)groups * R * S * Cout_g};
     cuuint64_t str[1] = {(cuuint64_t)Kp * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(cluster ? p.NT / 2 : p.NT)};
+    cuuint32_t box[2] = {64, (cuuint32_t)p.NT};
     if (!encode_bf16(&mB, w, 2, dims, str, box)) return VMGB_EINVAL;
   }
   const long long grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  if (use3x3 && cluster) {
-    const int smem = p.ra * p.a_unit_bytes + p.rb * p.b_stage_bytes + 1024 + 512 + 1024;
-    const long long n_mt = (long long)n_img * p.tiles_h * p.tiles_w;
-    const long long units = ((n_mt + 1) / 2) * groups * p.nt_per_g;
-    long long clusters = units < g_num_sms / 2 ? units : g_num_sms / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<true>, mA[0], mA[1], mA[2], mB, p);
-    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return VMGB_ECUDA; }
-  } else if (use3x3) {
-    const int smem = p.ra * p.a_unit_bytes + p.rb * p.b_stage_bytes + 1024 + 512 + 1024;
-    conv3x3_tc_kernel<false><<<(unsigned)grid, 256, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
-  } else {
-    const int smem = p.stages * (A_STAGE_BYTES + p.b_stage_bytes) + 1024 + 512 + 1024 + p.res_smem + p.out_smem + p.aux_smem;
-    conv_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
-  }
+  const int smem = p.stages * stage_bytes + 1024 + 512 + 1024 + epi_smem;
+  conv_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, as_stream(stream)>>>(mA[0], mA[1], mA[2], mB, p);
   return check_launch();
 }
