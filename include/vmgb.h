@@ -123,6 +123,15 @@ int vmgb_mix3(const void* h, const void* w, const void* c, int dt, const float* 
 int vmgb_ca_apply(const void* u, const void* x, int dt, const float* y, void* out, int out_dt,
                   int frames, long long rows_per_frame, int C, float scale, void* stream);
 
+/* lockstep sweep pairing of Trajectory_multi_head (trajectory.py:404-478: the backward and the forward sweep share
+ * their weights and only meet in the final fusion, so step j = [backward sweep at frame T-1-j | forward sweep at
+ * frame j] runs as one image batch).  x: T frames of frame_bytes; out: T steps of 2 frames.
+ *   pair  : out[j][0] = x[T-1-j], out[j][1] = x[j]
+ *   unpair: back[i] = paired[T-1-i][0] (= outputs_back[i]), fwd[i] = paired[i][1]
+ * frame_bytes and all pointers must be multiples of 16. */
+int vmgb_pair_sweeps(const void* x, void* out, int T, long long frame_bytes, void* stream);
+int vmgb_unpair_sweeps(const void* paired, void* back, void* fwd, int T, long long frame_bytes, void* stream);
+
 /* elementwise out = a + b */
 int vmgb_add(const void* a, const void* b, int dt, void* out, int out_dt, long long n, void* stream);
 

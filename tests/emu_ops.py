@@ -146,6 +146,19 @@ def ca_apply(u, x, y, rows_per_frame, scale):
     return ((uv * y[:, None, :] + x.float().reshape(-1, rows_per_frame, C)) * scale).reshape(u.shape).to(u.dtype)
 
 
+def pair_sweeps(x, T):
+    n = x.shape[0] // T
+    xs = x.view((T, n) + tuple(x.shape[1:]))
+    return torch.stack([xs.flip(0), xs], 1).reshape((T, 2 * n) + tuple(x.shape[1:])).contiguous()
+
+
+def unpair_sweeps(paired):
+    T, n = paired.shape[0], paired.shape[1] // 2
+    back = paired[:, :n].flip(0).reshape((T * n,) + tuple(paired.shape[2:])).contiguous()
+    fwd = paired[:, n:].reshape((T * n,) + tuple(paired.shape[2:])).contiguous()
+    return back, fwd
+
+
 def add(a, b):
     return (a.float() + b.float()).to(a.dtype)
 

@@ -143,6 +143,23 @@ def test_row_kernels(dtype, tol):
         A = ops.morph_gather(x4.to(DEV), chunk, axis)
         close(A, emu.morph_gather(x4, chunk, axis), 0)
         close(ops.morph_scatter(A, 3, 10, 14, 112, chunk, axis), x4, 0)     # permutation round trip
+    # narrow rows (C = 112: half-warp-per-row bf16 kernel), ragged row count
+    xn = rnd(1037, 112, seed=20).to(dtype)
+    close(ops.layernorm(xn.to(DEV), g[:112].to(DEV), b[:112].to(DEV)), emu.layernorm(xn, g[:112], b[:112]), tol)
+    # larger ragged Morph-FC case: several blocks per warp, H and W not multiples of the chunk
+    x5 = rnd(2, 21, 27, 112, seed=21).to(dtype)
+    for axis, chunk in ((0, 8), (1, 16), (0, 16), (1, 8)):
+        A = ops.morph_gather(x5.to(DEV), chunk, axis)
+        close(A, emu.morph_gather(x5, chunk, axis), 0)
+        close(ops.morph_scatter(A, 2, 21, 27, 112, chunk, axis), x5, 0)
+    # lockstep sweep pairing (pure data movement)
+    xt = rnd(5 * 2, 6, 7, 16, seed=22).to(dtype)
+    P = ops.pair_sweeps(xt.to(DEV), 5)
+    close(P, emu.pair_sweeps(xt, 5), 0)
+    bk, fw = ops.unpair_sweeps(P)
+    eb, ef = emu.unpair_sweeps(emu.pair_sweeps(xt, 5))
+    close(bk, eb, 0)
+    close(fw, ef, 0)
     h, w, c = (rnd(6, 8, 9, 112, seed=s).to(dtype) for s in (5, 6, 7))
     a = ops.channel_sum(h.to(DEV), w.to(DEV), c.to(DEV), 3, 2, 72, 1.0 / 216)
     a_ref = emu.channel_sum(h, w, c, 3, 2, 72, 1.0 / 216)

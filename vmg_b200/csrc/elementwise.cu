@@ -118,6 +118,103 @@ __global__ void __launch_bounds__(256) layernorm_narrow_kernel(const void* x, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lockstep sweep pairing of the trajectory (model.py _trajectory): pure 16-byte data movement.
+//   pair  : out[j][0] = x[T-1-j], out[j][1] = x[j]            (one read, two writes)
+//   unpair: back[i] = paired[T-1-i][0], fwd[i] = paired[i][1]
+// A "frame" is the n*H*W*C block of one time step.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pair_sweeps_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int T, long long fv) {
+  const long long total = (long long)T * fv;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const long long i = i0 + k * stride; if (i < total) v[k] = __ldg(x + i); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = i0 + k * stride;
+      if (i < total) {
+        const long long j = i / fv, r = i - j * fv;
+        out[(2 * j + 1) * fv + r] = v[k];
+        out[(2 * (T - 1 - j)) * fv + r] = v[k];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) unpair_sweeps_kernel(const uint4* __restrict__ paired, uint4* __restrict__ back,
+                                                            uint4* __restrict__ fwd, int T, long long fv) {
+  const long long total = 2LL * T * fv;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const long long i = i0 + k * stride; if (i < total) v[k] = __ldg(paired + i); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = i0 + k * stride;
+      if (i < total) {
+        const long long h = i / fv, r = i - h * fv;      // h = 2*j + half
+        const long long j = h >> 1;
+        if (h & 1) fwd[j * fv + r] = v[k];
+        else back[(T - 1 - j) * fv + r] = v[k];
+      }
+    }
+  }
+}
+
+// bf16 rows of up to 128 channels (C % 8 == 0): a HALF-warp owns a row, 16 bytes per lane, ROWS independent rows
+// in flight per half-warp (the 8-byte-per-lane kernel above leaves most of the HBM latency exposed: measured
+// 1.1 TB/s at C = 112)
+template <int ROWS>
+__global__ void __launch_bounds__(256) layernorm_half_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             long long rows, int C, float eps) {
+  const int hl = threadIdx.x & 15;
+  const long long hw_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const long long n_hw = ((long long)gridDim.x * blockDim.x) >> 4;
+  const int c = 8 * hl;
+  const bool act = c < C;
+  float g[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { g[k] = act ? gamma[c + k] : 0.f; b[k] = act ? beta[c + k] : 0.f; }
+  const float inv_c = 1.f / (float)C;
+  for (long long r0 = hw_id * ROWS; r0 < rows; r0 += n_hw * ROWS) {
+    uint4 raw[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k)
+      raw[k] = (act && r0 + k < rows) ? __ldg(reinterpret_cast<const uint4*>(x + (r0 + k) * C + c)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+      float v[8];
+      const uint32_t w[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { v[2 * q] = __uint_as_float(w[q] << 16); v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u); }
+      float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+#pragma unroll
+      for (int m = 8; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+      const float mean = s * inv_c;
+      float q2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { v[e] -= mean; q2 += v[e] * v[e]; }
+      q2 = act ? q2 : 0.f;
+#pragma unroll
+      for (int m = 8; m >= 1; m >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, m);
+      const float rstd = rsqrtf(q2 * inv_c + eps);
+      if (act && r0 + k < rows) {
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q] * rstd * g[2 * q] + b[2 * q], v[2 * q + 1] * rstd * g[2 * q + 1] + b[2 * q + 1]);
+          o[q] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(out + (r0 + k) * C + c) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
 // L2 normalise (F.normalize, eps 1e-12)
 __global__ void __launch_bounds__(256) l2norm_kernel(const void* x, int x_dt, int x_pitch, void* out, int out_dt,
                                                      long long rows, int C) {
@@ -245,6 +342,86 @@ __global__ void __launch_bounds__(32 * MORPH_WARPS) morph_block_kernel(const voi
           stf(dst, dst_dt, gi, sm[g * Cp + r * S + s2]);
         }
       }
+    }
+  }
+}
+
+// bf16 fast path of the block-staged permutation (C, Cp, a_pitch multiples of 8; 16-byte aligned tensors): both
+// global sides move 16 bytes per lane, the (r, g, s) <-> (g, r, s) shuffle happens on 2-byte elements in a bf16
+// shared-memory copy of the block, and the index arithmetic is incremental (the fp32-staged kernel above spends
+// ~4 integer divisions per 8 bytes and reached 0.6-1.2 TB/s).  Warps walk the blocks grid-stride.
+__global__ void __launch_bounds__(32 * MORPH_WARPS) morph_block16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                                        int BT, int H, int W, int C, int ch, int axis, int inverse,
+                                                                        long long n_blocks, int a_pitch) {
+  extern __shared__ uint4 sm_vec_all[];
+  const int Cp = (C + ch - 1) / ch * ch, S = Cp / ch;
+  const int L = axis == 0 ? H : W, Lg = (L + ch - 1) / ch, O = axis == 0 ? W : H;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int Cv = C >> 3, Cpv = Cp >> 3;
+  const int per_warp_vec = ch * (Cv > Cpv ? Cv : Cpv);
+  uint4* smv = sm_vec_all + wid * per_warp_vec;
+  const unsigned short* sme = reinterpret_cast<const unsigned short*>(smv);
+  const float inv_S = 1.f / (float)S, inv_Cv = 1.f / (float)Cv, inv_Cpv = 1.f / (float)Cpv;
+  const long long wstride = (long long)gridDim.x * MORPH_WARPS;
+  for (long long blk = (long long)blockIdx.x * MORPH_WARPS + wid; blk < n_blocks; blk += wstride) {
+    // block index = (bt*O + o)*Lg + lg  (same order as the row index / ch)
+    const int lg = (int)(blk % Lg); const long long t = blk / Lg; const int o = (int)(t % O); const int bt = (int)(t / O);
+    const long long rows0 = blk * ch;
+    if (!inverse) {
+      // 1. ch pixel rows -> sm[r*C + c]
+      for (int i = lane; i < ch * Cv; i += 32) {
+        const int r = (int)(((float)i + 0.5f) * inv_Cv), c8 = i - r * Cv;
+        const int l = lg * ch + r;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (l < L) {
+          const int h = axis == 0 ? l : o, w = axis == 0 ? o : l;
+          v = __ldg(reinterpret_cast<const uint4*>(src + (((long long)bt * H + h) * W + w) * C + 8 * c8));
+        }
+        smv[i] = v;
+      }
+      __syncwarp();
+      // 2. output vectors: element d = g*Cp + r*S + s  <-  sm[r*C + g*S + s]
+      for (int i = lane; i < ch * Cpv; i += 32) {
+        const int g = (int)(((float)i + 0.5f) * inv_Cpv), f = 8 * (i - g * Cpv);
+        int r = (int)(((float)f + 0.5f) * inv_S), s2 = f - r * S;
+        unsigned short e[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = g * S + s2;
+          e[k] = c < C ? sme[r * C + c] : (unsigned short)0;
+          if (++s2 == S) { s2 = 0; ++r; }
+        }
+        const uint4 v = make_uint4((uint32_t)e[0] | ((uint32_t)e[1] << 16), (uint32_t)e[2] | ((uint32_t)e[3] << 16),
+                                   (uint32_t)e[4] | ((uint32_t)e[5] << 16), (uint32_t)e[6] | ((uint32_t)e[7] << 16));
+        *reinterpret_cast<uint4*>(dst + (rows0 + g) * a_pitch + f) = v;
+      }
+      __syncwarp();
+    } else {
+      // 1. ch token rows -> sm[g*Cp + f]
+      for (int i = lane; i < ch * Cpv; i += 32) {
+        const int g = (int)(((float)i + 0.5f) * inv_Cpv), f8 = i - g * Cpv;
+        smv[i] = __ldg(reinterpret_cast<const uint4*>(src + (rows0 + g) * a_pitch + 8 * f8));
+      }
+      __syncwarp();
+      // 2. pixel-row vectors: element (r, c), c = g*S + s  <-  sm[g*Cp + r*S + s]
+      for (int i = lane; i < ch * Cv; i += 32) {
+        const int r = (int)(((float)i + 0.5f) * inv_Cv), c0 = 8 * (i - r * Cv);
+        const int l = lg * ch + r;
+        if (l < L) {
+          int g = (int)(((float)c0 + 0.5f) * inv_S), s2 = c0 - g * S;
+          unsigned short e[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            e[k] = sme[g * Cp + r * S + s2];
+            if (++s2 == S) { s2 = 0; ++g; }
+          }
+          const uint4 v = make_uint4((uint32_t)e[0] | ((uint32_t)e[1] << 16), (uint32_t)e[2] | ((uint32_t)e[3] << 16),
+                                     (uint32_t)e[4] | ((uint32_t)e[5] << 16), (uint32_t)e[6] | ((uint32_t)e[7] << 16));
+          const int h = axis == 0 ? l : o, w = axis == 0 ? o : l;
+          *reinterpret_cast<uint4*>(dst + (((long long)bt * H + h) * W + w) * C + c0) = v;
+        }
+      }
+      __syncwarp();
     }
   }
 }
@@ -504,7 +681,12 @@ extern "C" int vmgb_layernorm(const void* x, int x_dt, void* out, int out_dt, co
   if (!x || !out || !gamma || !beta || !dt_ok(x_dt) || !dt_ok(out_dt) || C <= 0 || C > 32 * MAXV || rows <= 0) return VMGB_EINVAL;
   long long blocks = (rows + 7) / 8;
   const bool vec = (C & 3) == 0 && !((uintptr_t)x & 15) && !((uintptr_t)out & 15) && !((uintptr_t)gamma & 15) && !((uintptr_t)beta & 15);
-  if (vec && C <= 128) {
+  if (vec && C <= 128 && (C & 7) == 0 && x_dt == VMGB_BF16 && out_dt == VMGB_BF16) {
+    const long long wanted = (rows + 16 * 8 - 1) / (16 * 8);          // 16 half-warps per block, 8 rows each per iteration
+    const unsigned nb = (unsigned)(wanted < 148 * 6 ? (wanted < 1 ? 1 : wanted) : 148 * 6);
+    layernorm_half_kernel<8><<<nb, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, (const float*)gamma,
+                                                                 (const float*)beta, rows, C, eps);
+  } else if (vec && C <= 128) {
     const long long wanted = (rows + 8 * 4 - 1) / (8 * 4);
     const unsigned nb = (unsigned)(wanted < 148 * 8 ? (wanted < 1 ? 1 : wanted) : 148 * 8);
     layernorm_narrow_kernel<4><<<nb, 256, 0, as_stream(stream)>>>(x, x_dt, out, out_dt, (const float*)gamma, (const float*)beta, rows, C, eps);
@@ -530,6 +712,16 @@ extern "C" int vmgb_morph_permute(const void* src, int src_dt, void* dst, int ds
   const int Cp = (C + chunk - 1) / chunk * chunk;
   if (a_pitch < Cp) return VMGB_EINVAL;
   const int L = axis == 0 ? H : W, Lp = (L + chunk - 1) / chunk * chunk, O = axis == 0 ? W : H;
+  const long long n_blocks_all = (long long)BT * O * (Lp / chunk);
+  if (src_dt == VMGB_BF16 && dst_dt == VMGB_BF16 && (C & 7) == 0 && (Cp & 7) == 0 && (a_pitch & 7) == 0 &&
+      !(((uintptr_t)src | (uintptr_t)dst) & 15) && (size_t)chunk * Cp * 2 * MORPH_WARPS <= 48 * 1024 && Cp < 4096) {
+    const size_t smem = (size_t)chunk * Cp * 2 * MORPH_WARPS;        // C <= Cp
+    const long long wanted = (n_blocks_all + MORPH_WARPS - 1) / MORPH_WARPS;
+    const unsigned grid = (unsigned)(wanted < 148 * 16 ? wanted : 148 * 16);
+    morph_block16_kernel<<<grid, 32 * MORPH_WARPS, smem, as_stream(stream)>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, BT, H, W, C, chunk,
+                                                                            axis, inverse, n_blocks_all, a_pitch);
+    return check_launch();
+  }
   const size_t per_warp = (size_t)chunk * Cp * sizeof(float);
   int warps = (int)((48 * 1024) / per_warp);
   if (warps > MORPH_WARPS) warps = MORPH_WARPS;
@@ -594,6 +786,25 @@ extern "C" int vmgb_ca_apply(const void* u, const void* x, int dt, const float* 
     ca_apply_vec_kernel<<<grid_for(total / 4, 256, 148 * 32), 256, 0, as_stream(stream)>>>(u, x, dt, y, out, out_dt, rows_per_frame, C / 4, scale, total / 4);
   else
   ca_apply_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(u, x, dt, y, out, out_dt, rows_per_frame, C, scale, total);
+  return check_launch();
+}
+
+extern "C" int vmgb_pair_sweeps(const void* x, void* out, int T, long long frame_bytes, void* stream) {
+  if (!x || !out || T <= 0 || frame_bytes <= 0 || (frame_bytes & 15) || ((uintptr_t)x & 15) || ((uintptr_t)out & 15)) return VMGB_EINVAL;
+  const long long fv = frame_bytes / 16, total = (long long)T * fv;
+  const long long wanted = (total + 1023) / 1024;
+  pair_sweeps_kernel<<<(unsigned)(wanted < 148 * 8 ? wanted : 148 * 8), 256, 0, as_stream(stream)>>>((const uint4*)x, (uint4*)out, T, fv);
+  return check_launch();
+}
+
+extern "C" int vmgb_unpair_sweeps(const void* paired, void* back, void* fwd, int T, long long frame_bytes, void* stream) {
+  if (!paired || !back || !fwd || T <= 0 || frame_bytes <= 0 || (frame_bytes & 15) || ((uintptr_t)paired & 15) || ((uintptr_t)back & 15) ||
+      ((uintptr_t)fwd & 15))
+    return VMGB_EINVAL;
+  const long long fv = frame_bytes / 16, total = 2LL * T * fv;
+  const long long wanted = (total + 1023) / 1024;
+  unpair_sweeps_kernel<<<(unsigned)(wanted < 148 * 8 ? wanted : 148 * 8), 256, 0, as_stream(stream)>>>((const uint4*)paired, (uint4*)back,
+                                                                                                     (uint4*)fwd, T, fv);
   return check_launch();
 }
 

@@ -416,12 +416,9 @@ class VMG(nn.Module):
         tm = st.traj_mixing
         N, H, W, C = x.shape
         n = B
-        xs = x.view(T, n, H, W, C)
-        qn = o.l2norm(x).view(T, n, H, W, C)            # queries; a key frame's keys are its own normalised input
         # paired, step-major copies (pure data movement): [T, 2n, H, W, C]
-        xp = torch.stack([xs.flip(0), xs], 1).reshape(T, 2 * n, H, W, C)
-        qp = torch.stack([qn.flip(0), qn], 1).reshape(T, 2 * n, H, W, C)
-        del qn
+        xp = o.pair_sweeps(x, T)
+        qp = o.pair_sweeps(o.l2norm(x), T)              # queries; a key frame's keys are its own normalised input
         # step j >= 1: backward sweep uses flows_backward[:, T-1-j], forward sweep flows_forward[:, j-1]
         fl = torch.stack([flows_b.flip(0), flows_f], 1).reshape(T - 1, 2 * n, H, W, 2) if T > 1 else None
         stride = st.key_stride
@@ -451,8 +448,7 @@ class VMG(nn.Module):
             if is_key:
                 K += 1                                  # step j becomes key frame K-1 once fbuf[j] is written
             prev = self._resblocks(tm.resblocks, (xp[j], feat_in), fbuf[j])
-        back = fbuf[:, :n].flip(0).contiguous().view(N, H, W, C)  # outputs_back[i] = backward sweep at step T-1-i
-        fwd = fbuf[:, n:].contiguous().view(N, H, W, C)
+        back, fwd = o.unpair_sweeps(fbuf)               # outputs_back[i] = backward sweep at step T-1-i
         return o.conv2d((back, x, fwd), self._pc(tm.fusion), act=o.ACT_LRELU, alpha=0.1)
 
     # -------------------------------------------------------------------------------------------

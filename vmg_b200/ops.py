@@ -317,6 +317,28 @@ def ca_apply(u, x, y, rows_per_frame, scale):
     return out
 
 
+def pair_sweeps(x, T):
+    """x [T*n, ...] time-major -> [T, 2n, ...]: step j = [x[T-1-j] | x[j]] (both trajectory sweeps in lockstep)."""
+    require_device()
+    assert x.is_contiguous() and x.shape[0] % T == 0
+    n = x.shape[0] // T
+    out = torch.empty((T, 2 * n) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+    _ck(lib().vmgb_pair_sweeps(x.data_ptr(), out.data_ptr(), T, x.numel() // T * x.element_size(), _stream()), 'vmgb_pair_sweeps')
+    return out
+
+
+def unpair_sweeps(paired):
+    """paired [T, 2n, ...] -> (back, fwd), each [T*n, ...]: back[i] = paired[T-1-i, :n], fwd[i] = paired[i, n:]."""
+    require_device()
+    assert paired.is_contiguous() and paired.shape[1] % 2 == 0
+    T, n = paired.shape[0], paired.shape[1] // 2
+    back = torch.empty((T * n,) + tuple(paired.shape[2:]), device=paired.device, dtype=paired.dtype)
+    fwd = torch.empty_like(back)
+    fb = paired.numel() // (2 * T) * paired.element_size()
+    _ck(lib().vmgb_unpair_sweeps(paired.data_ptr(), back.data_ptr(), fwd.data_ptr(), T, fb, _stream()), 'vmgb_unpair_sweeps')
+    return back, fwd
+
+
 def add(a, b):
     require_device()
     assert a.shape == b.shape and a.dtype == b.dtype and a.is_contiguous() and b.is_contiguous()
