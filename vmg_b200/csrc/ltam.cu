@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(128) ltam_wins_kernel(const void* q, const voi
 // across key frames) and every (head, query) thread then reads its head segment from shared memory.  The
 // direct version above issues 8-byte loads per thread and re-reads each row through L1 for the 4 queries.
 // ---------------------------------------------------------------------------------------------
+constexpr int LTAM_STAGES = 3;
 template <int D4>
 __global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ keys,
                                                              const __nv_bfloat16* __restrict__ vals, long long kv_stride,
@@ -92,7 +93,9 @@ __global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16
                                                              const float* __restrict__ decay, void* out, int out_dt, int n, int h, int w,
                                                              int K, long long n_windows) {
   constexpr int D = D4 * 4, C = 4 * D, ROWB = C * 2, CH = ROWB / 16;     // bytes / 16-byte chunks per row
-  extern __shared__ __align__(16) uint8_t sm[];                           // [2 stages][2 (k,v)][32 rows][ROWB]
+  constexpr int NST = LTAM_STAGES;
+  extern __shared__ __align__(16) uint8_t sm[];                           // [NST stages][2 (k,v)][32 rows][ROWB], then src_s[32][K]
+  int* src_s = reinterpret_cast<int*>(sm + NST * (2 * 32 * ROWB));        // gathered source pixel of (row, key frame), -1 = outside
   const int tid = threadIdx.x;
   const long long win0 = (long long)blockIdx.x * 8;
   const int wl = tid >> 4, sub = tid & 15, head = sub >> 2, qi = sub & 3;
@@ -105,6 +108,19 @@ __global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16
   const long long qpix = pix0 + (qi >> 1) * w + (qi & 1);
   const float scale = rsqrtf((float)D);
 
+  // the sampling locations of all key frames first (one dependent global round trip per block instead of one per
+  // key frame): src_s[r*K + k] = pixel index inside the key frame, or -1 (padding_mode='zeros')
+  for (int idx = tid; idx < 32 * K; idx += 128) {
+    const int r = idx / K, k = idx - r * K;                  // r = window-local row: (window r>>2, position r&3)
+    long long wn = win0 + (r >> 2);
+    if (wn >= n_windows) wn = n_windows - 1;
+    const int x2 = (int)(wn % ww); const long long t2 = wn / ww; const int y2 = (int)(t2 % wh); const int i2 = (int)(t2 / wh);
+    const long long pj = ((long long)i2 * h + 2 * y2 + ((r & 3) >> 1)) * w + 2 * x2 + (r & 1);
+    const float2 lc = *reinterpret_cast<const float2*>(loc + pj * loc_pitch + 2 * k);
+    const int sx = (int)rintf(lc.x), sy = (int)rintf(lc.y);
+    src_s[idx] = (sx >= 0 && sx < w && sy >= 0 && sy < h) ? (int)(((long long)i2 * h + sy) * w + sx) : -1;
+  }
+
   float qv[D], acc[D];
 #pragma unroll
   for (int i = 0; i < D4; ++i) {
@@ -116,39 +132,44 @@ __global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16
   float relq[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) relq[j] = rel[(head * 4 + qi) * 4 + j];
+  __syncthreads();
 
   // stage one key frame: 32 rows x CH chunks for keys and the same for values
   auto stage = [&](int k, int buf) {
     uint8_t* base = sm + buf * (2 * 32 * ROWB);
     for (int c = tid; c < 32 * CH; c += 128) {
-      const int r = c / CH, cc = c - r * CH;               // r = window-local row: (window r>>2, position r&3)
-      long long wn = win0 + (r >> 2);
-      if (wn >= n_windows) wn = n_windows - 1;
-      const int x2 = (int)(wn % ww); const long long t2 = wn / ww; const int y2 = (int)(t2 % wh); const int i2 = (int)(t2 / wh);
-      const long long pj = ((long long)i2 * h + 2 * y2 + ((r & 3) >> 1)) * w + 2 * x2 + (r & 1);
-      const float2 lc = *reinterpret_cast<const float2*>(loc + pj * loc_pitch + 2 * k);
-      const int sx = (int)rintf(lc.x), sy = (int)rintf(lc.y);
+      const int r = c / CH, cc = c - r * CH;
+      const int sp = src_s[r * K + k];
       const uint32_t dk = (uint32_t)__cvta_generic_to_shared(base + r * ROWB + cc * 16);
       const uint32_t dv = dk + 32 * ROWB;
-      if (sx >= 0 && sx < w && sy >= 0 && sy < h) {
-        const long long src = (long long)k * kv_stride + (((long long)i2 * h + sy) * w + sx) * C + cc * 8;
+      if (sp >= 0) {
+        const long long src = (long long)k * kv_stride + (long long)sp * C + cc * 8;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dk), "l"(keys + src) : "memory");
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dv), "l"(vals + src) : "memory");
-      } else {                                              // padding_mode='zeros'
+      } else {
         asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dk), "r"(0) : "memory");
         asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dv), "r"(0) : "memory");
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
   float m = -INFINITY, l = 0.f, pe = 1.f;
-  stage(K - 1, 0);
+  // NST-deep ring over the key frames (newest first); one commit group per iteration, empty groups at the tail
+#pragma unroll
+  for (int sidx = 0; sidx < NST - 1; ++sidx) {
+    if (K - 1 - sidx >= 0) stage(K - 1 - sidx, sidx);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   int buf = 0;
-  for (int k = K - 1; k >= 0; --k, buf ^= 1) {
-    if (k > 0) stage(k - 1, buf ^ 1);
-    if (k > 0) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
+  for (int k = K - 1; k >= 0; --k) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");      // key frame k has landed (this thread's part)
+    __syncthreads();                                        // ... everyone's part; and everyone is done with the buffer of k+1
+    {
+      const int kn = k - (NST - 1);
+      int bn = buf + NST - 1; if (bn >= NST) bn -= NST;
+      if (kn >= 0) stage(kn, bn);                            // re-fills the buffer consumed in the previous iteration
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     pe *= dh;
     const uint8_t* base = sm + buf * (2 * 32 * ROWB);
 #pragma unroll
@@ -175,7 +196,7 @@ __global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16
         acc[4 * i + 3] = acc[4 * i + 3] * corr + pw * vv.w;
       }
     }
-    __syncthreads();                                        // this buffer is re-filled two iterations later
+    if (++buf == NST) buf = 0;
   }
   if (!active) return;
   const float inv = 1.f / l;
@@ -198,11 +219,13 @@ extern "C" int vmgb_ltam_wins(const void* q, const void* keys, const void* vals,
   const unsigned blocks = (unsigned)((n_windows + 7) / 8);
   const int D4 = C / heads / 4;
   if (dt == VMGB_BF16 && !(((uintptr_t)keys | (uintptr_t)vals) & 15) && (kv_stride & 7) == 0 && (D4 == 7 || D4 == 9)) {
-    const int smem = 2 * 2 * 32 * C * 2;
+    const int smem = LTAM_STAGES * 2 * 32 * C * 2 + 32 * K * 4;
+    if (smem > 200 * 1024) return VMGB_EUNSUPPORTED;
 #define LAUNCH_S(DD)                                                                                                          \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(ltam_wins_smem_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);         \
     ltam_wins_smem_kernel<DD><<<blocks, 128, smem, as_stream(stream)>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)keys,  \
         (const __nv_bfloat16*)vals, kv_stride, loc, loc_pitch, rel, decay, out, out_dt, n, h, w, K, n_windows)
-    if (D4 == 7) LAUNCH_S(7); else LAUNCH_S(9);
+    if (D4 == 7) { LAUNCH_S(7); } else { LAUNCH_S(9); }
 #undef LAUNCH_S
     return check_launch();
   }
