@@ -89,6 +89,10 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
+// programmatic dependent launch: the next kernel of the stream may start its prologue (barriers, TMEM, weight loads)
+// while this one drains; it must not touch anything a predecessor writes (or still reads) before pdl_wait()
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -222,16 +226,23 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return q;
 }
 
-// exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|erf error| <= 1.5e-7, far below bf16 resolution) on
-// the two single-instruction SFU approximations rcp.approx / ex2.approx: 2 MUFU + ~10 FMA per element.  The FFN
-// fc1 epilogue evaluates ~4e9 GELUs per clip and was ALU-bound on the branchy ~40-instruction erff().
+// exact-erf GELU with erf from Abramowitz & Stegun 7.1.28: erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16, |error| <= 3e-7
+// (far below bf16 resolution), z = |x|/sqrt(2).  One MUFU (rcp.approx) + ~14 FMA-class operations per element; the
+// FFN fc1 epilogue evaluates ~4e9 GELUs per clip and is bound by exactly these two pipes (the 7.1.26 form needs a
+// second MUFU for exp(-z^2), erff() is a branchy ~40 instructions).  A polynomial that overflows (|x| > ~25)
+// gives rcp(inf) = 0, i.e. erf = 1, which is the correct limit.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
-  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-  const float erf_abs = fmaf(-poly, e, 1.f);               // erf(|x|/sqrt2)
+  float p = fmaf(z, 0.0000430638f, 0.0002765672f);
+  p = fmaf(z, p, 0.0001520143f);
+  p = fmaf(z, p, 0.0092705272f);
+  p = fmaf(z, p, 0.0422820123f);
+  p = fmaf(z, p, 0.0705230784f);
+  p = fmaf(z, p, 1.f);
+  p *= p; p *= p; p *= p; p *= p;                            // ^16
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+  const float erf_abs = 1.f - r;                             // erf(|x|/sqrt2)
   const float hx = 0.5f * x;
   return fmaf(fabsf(hx), erf_abs, hx);                      // 0.5*x*(1 + sign(x)*erf_abs) = hx + |hx|*erf_abs
 }
@@ -570,9 +581,11 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
                                                  uint32_t tempty_cluster0) {
   const int ew = warp - 4, quarter = warp & 3, half = ew >> 2;
   const int row = quarter * 32 + lane;
-  const int nchunks = p.NT >> 4, ngroups = (p.NT + 63) >> 6;
+  const int nchunks = p.NT >> 4;
+  // this warp's 16-column chunks: the two column halves split the accumulator evenly; a pass covers <= 4 chunks (64 columns)
+  const int c_lo = half ? (nchunks + 1) >> 1 : 0, c_hi = half ? nchunks : (nchunks + 1) >> 1;
   const int epi = EPI < 0 ? p.epi : EPI;
-  const bool has_res = epi != VMGB_EPI_STORE;          // host: bf16 residual, 16-byte aligned rows, NT <= 128 (one group per warp)
+  const bool has_res = epi != VMGB_EPI_STORE;          // host: bf16 residual, 16-byte aligned rows, NT <= 128 (one pass per warp)
   const uint32_t buf = smem_u32(bias_s) + 1024 + (uint32_t)ew * 4096u;
   const int bw_shift = 31 - __clz(p.BW), bw_mask = p.BW - 1;
   const int crow0 = lane >> 3, piece = lane & 7;
@@ -581,19 +594,21 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
   uint32_t acc_phase0 = 0, acc_phase1 = 0;
   int it = 0, bias_combo = -1;
 
-  auto prefetch_res = [&](long long t, int grp) {
+  // coalesced side of one pass starting at chunk ch0: column of this lane's 16-byte piece and whether it exists
+  auto prefetch_res = [&](long long t, int ch0, int chn) {
     int combo, img, h0, w0; bool tvalid;
     origin(t, combo, img, h0, w0, tvalid);
     const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
-    const int col = grp * 64 + piece * 8;
-    const bool cok = tvalid && col < p.NT && nt * p.NT + col + 8 <= p.Cout_g;
+    const int col = ch0 * 16 + piece * 8;
+    const bool cok = tvalid && piece < 2 * chn && nt * p.NT + col + 8 <= p.Cout_g;
+    const long long pbase = ((long long)img * p.H + h0) * p.W + w0;
+    const __nv_bfloat16* rp0 = resp + g * p.Cout_g + nt * p.NT + col;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = crow0 + 4 * i, rr = quarter * 32 + r;
-      const int hh = h0 + (rr >> bw_shift), ww = w0 + (rr & bw_mask);
-      if (cok && hh < p.H && ww < p.W) {
-        const long long pix = ((long long)img * p.H + hh) * p.W + ww;
-        const __nv_bfloat16* rp = resp + pix * p.res_pitch + g * p.Cout_g + nt * p.NT + col;
+      const int dh = rr >> bw_shift, dw = rr & bw_mask;
+      if (cok && h0 + dh < p.H && w0 + dw < p.W) {
+        const __nv_bfloat16* rp = rp0 + (pbase + (long long)dh * p.W + dw) * p.res_pitch;
         const uint32_t dst = buf + (uint32_t)r * 128u + (uint32_t)((piece ^ (r & 7)) << 4);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rp) : "memory");
       }
@@ -601,7 +616,7 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  if (has_res && half < ngroups && first < total) prefetch_res(first, half);
+  if (has_res && c_lo < c_hi && first < total) prefetch_res(first, c_lo, c_hi - c_lo);
   for (long long t = first; t < total; t += step, ++it) {
     const int as = it & 1;
     int combo, img, h0, w0; bool tvalid;
@@ -609,6 +624,7 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
     const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
     const int hh = h0 + (row >> bw_shift), ww = w0 + (row & bw_mask);
     const bool pvalid = tvalid && hh < p.H && ww < p.W;
+    const long long pbase = ((long long)img * p.H + h0) * p.W + w0;
     const long long pix = ((long long)img * p.H + hh) * p.W + ww;
     const uint32_t aph = as ? acc_phase1 : acc_phase0;
     if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
@@ -622,7 +638,7 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
       asm volatile("bar.sync 1, 256;" ::: "memory");
       bias_combo = combo;
     }
-    if (has_res) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); }     // this item's residual group has landed
+    if (has_res) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); }     // this item's residual pass has landed
     mbar_wait(tfull0 + 8 * as, aph);
     tc_fence_after();
     if (p.dbg & 2) {
@@ -632,8 +648,9 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
     }
     const uint32_t rowbase = buf + (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
-    for (int grp = half; grp < ngroups; grp += 2) {
-      const int ch0 = grp * 4, chn = min(4, nchunks - ch0);
+    __nv_bfloat16* op0 = outp + g * p.Cout_g + nt * p.NT;
+    for (int ch0 = c_lo; ch0 < c_hi; ch0 += 4) {
+      const int chn = min(4, c_hi - ch0);
       auto process = [&](int c, const uint32_t* raw) {
         const uint32_t c0 = rowbase + (((uint32_t)(2 * c) ^ sw) << 4), c1 = rowbase + (((uint32_t)(2 * c + 1) ^ sw) << 4);
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
@@ -659,33 +676,32 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
         if (c + 2 < chn) tmem_ld16_issue(taddr + (ch0 + c + 2) * 16, rawA);
         process(c + 1, rawB);
       }
-      if (grp + 2 >= ngroups) {           // last TMEM read of this item: hand the accumulator back before the copy-out
+      if (ch0 + 4 >= c_hi) {              // last TMEM read of this item: hand the accumulator back before the copy-out
         tc_fence_before();
         if (tempty_cluster0) mbar_arrive_cluster(tempty_cluster0 + 8 * as); else mbar_arrive(tempty0 + 8 * as);
       }
       __syncwarp();
-      // coalesced copy-out of the group: 4 rows x 128 contiguous bytes per warp instruction
-      const int col = grp * 64 + piece * 8;
-      const bool cok = tvalid && col < p.NT && nt * p.NT + col + 8 <= p.Cout_g && !(p.dbg & 8);
+      // coalesced copy-out of the pass: 4 rows x (up to) 128 contiguous bytes per warp instruction
+      const int col = ch0 * 16 + piece * 8;
+      const bool cok = tvalid && piece < 2 * chn && nt * p.NT + col + 8 <= p.Cout_g && !(p.dbg & 8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = crow0 + 4 * i, rr = quarter * 32 + r;
-        const int h2 = h0 + (rr >> bw_shift), w2 = w0 + (rr & bw_mask);
-        if (cok && h2 < p.H && w2 < p.W) {
+        const int dh = rr >> bw_shift, dw = rr & bw_mask;
+        if (cok && h0 + dh < p.H && w0 + dw < p.W) {
           uint4 val;
           const uint32_t src = buf + (uint32_t)r * 128u + (uint32_t)((piece ^ (r & 7)) << 4);
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(src) : "memory");
-          const long long o = (((long long)img * p.H + h2) * p.W + w2) * p.out_pitch + g * p.Cout_g + nt * p.NT + col;
-          *reinterpret_cast<uint4*>(outp + o) = val;
+          *reinterpret_cast<uint4*>(op0 + (pbase + (long long)dh * p.W + dw) * p.out_pitch + col) = val;
         }
       }
-      __syncwarp();                       // buffer free: next group / next item's residual
+      __syncwarp();                       // buffer free: next pass / next item's residual
     }
-    if (half >= ngroups) {                // idle column half (NT <= 64): still a party of the accumulator hand-back
+    if (c_lo >= c_hi) {                   // idle column half (NT = 16): still a party of the accumulator hand-back
       tc_fence_before();
       if (tempty_cluster0) mbar_arrive_cluster(tempty_cluster0 + 8 * as); else mbar_arrive(tempty0 + 8 * as);
     }
-    if (has_res && half < ngroups && t + step < total) prefetch_res(t + step, half);
+    if (has_res && c_lo < c_hi && t + step < total) prefetch_res(t + step, c_lo, c_hi - c_lo);
   }
 }
 
@@ -1058,16 +1074,17 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   const uint32_t w_base = a_base + p.ra * p.a_unit_bytes;
   const uint32_t bar_base = (w_base + nboxes * p.b_stage_bytes + 1023u) & ~1023u;
   const uint32_t afull0 = bar_base, aempty0 = afull0 + 8 * p.ra;
-  const uint32_t wfull = aempty0 + 8 * p.ra;
-  const uint32_t tfull0 = wfull + 16, tempty0 = tfull0 + 16;
+  const uint32_t wfull0 = aempty0 + 8 * p.ra;          // one barrier per weight box (<= 27): the first tile starts on tap 0's weights
+  const uint32_t tfull0 = wfull0 + 8 * 28, tempty0 = tfull0 + 16;
   const uint32_t tmem_slot = tempty0 + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.ra; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
-    mbar_init(wfull, 1);
+    for (int i = 0; i < nboxes; ++i) mbar_init(wfull0 + 8 * i, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 512); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -1084,10 +1101,11 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   float* bias_s = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
 
   const int tiles_per_img = p.tiles_h * p.tiles_w;
-  const int ncombo = p.nt_per_g;                      // groups == 1
+  const int ncombo = p.groups * p.nt_per_g;
   const long long cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   const int combo = (int)(cl % ncombo);
-  const int nt = combo;
+  const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+  const int koff = (g * p.Cin_g) & 7;                 // grouped conv: the channel box starts 16-byte aligned, the packed weights are shifted alike
   const long long first = cl / ncombo, step = ncl / ncombo;
   const long long n_mt = (long long)p.n_img * tiles_per_img;
   const long long n_pairs = (n_mt + 1) >> 1;
@@ -1095,14 +1113,18 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    const uint32_t wfull_l = mapa_rank(wfull, 0), afull0_l = mapa_rank(afull0, 0);
-    if (elect_one()) {                 // this CTA's half of the weight slice, once
-      if (rank == 0) mbar_expect_tx(wfull, (uint32_t)(2 * nboxes * NH * 128));
+    const uint32_t wfull0_l = mapa_rank(wfull0, 0), afull0_l = mapa_rank(afull0, 0);
+    if (elect_one()) {                 // this CTA's half of the weight slice, once, in the order the MMAs consume it
       for (int kb = 0; kb < p.kb_per_src; ++kb)
-        for (int tap = 0; tap < TAPS; ++tap)
-          tma_load_2d_2sm(w_base + (kb * TAPS + tap) * p.b_stage_bytes, &mapB, wfull_l, kb * 64, tap * p.Cout_g + nt * p.NT + (int)rank * NH);
+        for (int tap = 0; tap < TAPS; ++tap) {
+          const int box = kb * TAPS + tap;
+          if (rank == 0) mbar_expect_tx(wfull0 + 8 * box, (uint32_t)(2 * NH * 128));
+          tma_load_2d_2sm(w_base + box * p.b_stage_bytes, &mapB, wfull0_l + 8 * box, kb * 64,
+                          (g * TAPS + tap) * p.Cout_g + nt * p.NT + (int)rank * NH);
+        }
     }
     __syncwarp();
+    pdl_wait();                        // the weights are static; the activations come from the previous kernel
     int ia = 0; uint32_t pa = 0;
     constexpr uint32_t a_bytes = (uint32_t)UROWS * BWX * 128;
     for (long long t = first; t < n_pairs; t += step) {
@@ -1118,7 +1140,7 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           if (p.dbg & 4) { if (rank == 0) mbar_arrive(afull0 + 8 * ia); }
           else {
             if (rank == 0) mbar_expect_tx(afull0 + 8 * ia, 2 * a_bytes);
-            tma_load_4d_2sm(a_base + ia * p.a_unit_bytes, &mapA, afull0_l + 8 * ia, kb * 64, w0 - 1, h0 - 1, img);
+            tma_load_4d_2sm(a_base + ia * p.a_unit_bytes, &mapA, afull0_l + 8 * ia, ((g * p.Cin_g) & ~7) + kb * 64, w0 - 1, h0 - 1, img);
           }
         }
         __syncwarp();
@@ -1132,8 +1154,6 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     uint32_t acc_phase0 = 0, acc_phase1 = 0;
     int it = 0;
     const uint32_t issue = elect_one() ? 1u : 0u;        // one fixed lane issues every tcgen05 instruction of this warp
-    mbar_wait(wfull, 0);
-    tc_fence_after();
     for (long long t = first; t < n_pairs; t += step, ++it) {
       const int as = it & 1;
       const uint32_t aph = as ? acc_phase1 : acc_phase0;
@@ -1143,13 +1163,14 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
       uint32_t accumulate = 0;
       for (int kb = 0; kb < p.kb_per_src; ++kb) {
-        const int nks = min(4, (p.Cs - kb * 64 + 15) >> 4);
+        const int nks = min(4, (p.Cs + koff - kb * 64 + 15) >> 4);
         mbar_wait(afull0 + 8 * ia, pa);
         tc_fence_after();
         const uint32_t a_unit = a_base + ia * p.a_unit_bytes;
         if (!(p.dbg & 1)) {
 #pragma unroll
           for (int tap = 0; tap < TAPS; ++tap) {
+            if (it == 0) { mbar_wait(wfull0 + 8 * (kb * TAPS + tap), 0); tc_fence_after(); }     // weights of this box have landed (first tile only)
             const uint64_t ad = smem_desc_sw128_sbo(a_unit + (uint32_t)((tap / RR) * BWX + (tap % RR)) * 128u, (uint32_t)BWX * 128u);
             const uint64_t bd = smem_desc_sw128(w_base + (kb * TAPS + tap) * p.b_stage_bytes);
             for (int ks = 0; ks < nks; ++ks)
@@ -1165,6 +1186,7 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps per CTA, each CTA drains its own 128 accumulator rows) =====================
+    pdl_wait();                        // residual reads and output writes wait for the predecessors
     if (p.wst)
       run_epilogue_w(p, bias_s, tmem_base, tfull0, tempty0, first, step, n_pairs, warp, lane,
                      [&](long long t, int& cmb, int& img, int& h0, int& w0, bool& valid) {
@@ -1209,6 +1231,7 @@ static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 0;
 static int g_smem_optin = 0;
 static std::once_flag g_once;
+static int g_pdl = 1;         // VMGB_PDL=0 turns programmatic dependent launch off
 static int g_no_wst = 0;      // VMGB_NO_WST=1: A/B switch (tools/microbench.py) for the warp-private staging epilogue
 
 static void tc_init() {
@@ -1216,7 +1239,8 @@ static void tc_init() {
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
     g_encode = (EncodeTiledFn)fn;
-  if (const char* e = getenv("VMGB_NO_WST")) g_no_wst = atoi(e);      // A/B switch for tools/microbench.py
+  if (const char* e = getenv("VMGB_NO_WST")) g_no_wst = atoi(e);
+  if (const char* e = getenv("VMGB_PDL")) g_pdl = atoi(e);      // A/B switch for tools/microbench.py
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1247,7 +1271,7 @@ static bool wst_ok(int NT, int Cout_g, const void* out, int out_dt, int out_pitc
   if (g_no_wst) return false;
   if (out_dt != VMGB_BF16 || ps != 0 || (out_pitch & 7) || (Cout_g & 7) || (reinterpret_cast<uintptr_t>(out) & 15)) return false;
   if (epi == VMGB_EPI_STORE) return true;
-  return epi == VMGB_EPI_RESADD && res_dt == VMGB_BF16 && !(res_pitch & 7) && !(reinterpret_cast<uintptr_t>(res) & 15) && NT <= 128;
+  return epi == VMGB_EPI_RESADD && res_dt == VMGB_BF16 && !(res_pitch & 7) && !(reinterpret_cast<uintptr_t>(res) & 15) && NT <= 128;      // one pass per warp
 }
 
 }  // namespace vmgb
@@ -1291,9 +1315,9 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0; p.res_smem = 0; p.out_smem = 0; p.aux_smem = 0;
   const int budget = g_smem_optin - 1024 - 512 - 1024;     // alignment slack, barriers, bias staging
 
-  // ---- CTA-pair weight-stationary 3x3 kernel (variant 13, or auto): single source, ungrouped
+  // ---- CTA-pair weight-stationary 3x3 kernel (variant 13, or auto): single source (grouped or not)
   if (variant >= 32) { p.dbg = (variant >> 5) & 15; variant = 13; }      // probes: 13 + 32*dbg
-  if (R == 3 && S == 3 && H >= 8 && W >= 8 && n_src == 1 && groups == 1 && (variant == 0 || variant == 13)) {
+  if (R == 3 && S == 3 && H >= 8 && W >= 8 && n_src == 1 && (variant == 0 || variant == 13)) {
     const int ubytes = (18 * 10 * 128 + 1023) / 1024 * 1024;
     const int nboxes = 9 * p.kb_per_src;                  // SWIZZLE_128B weight boxes {64 k, NT/2 rows}
     const long long n_mt = (long long)n_img * ((H + 15) / 16) * ((W + 7) / 8);
@@ -1305,8 +1329,10 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       const int wbytes = (nboxes * (nts / 2) * 128 + 1023) / 1024 * 1024;
       const int old_resb = (epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0) ? nts * 256 : 0;
       // the warp-private staging epilogue only where it does not cost an activation ring slot
+      // (wide outputs were copied out through a whole-tile staging buffer whose index arithmetic cost more than the GELU)
       const bool wst = wst_ok(nts, Cout_g, out, out_dt, out_pitch, pixel_shuffle, epi, res, res_dt, res_pitch) &&
-                       (budget - wbytes - WST_BYTES) / ubytes >= 3 && (budget - wbytes - WST_BYTES) / ubytes >= (budget - wbytes - old_resb) / ubytes;
+                       (budget - wbytes - WST_BYTES) / ubytes >= 3 &&
+                       (Cout >= 256 || (budget - wbytes - WST_BYTES) / ubytes >= (budget - wbytes - old_resb) / ubytes);
       const int resb = wst ? WST_BYTES : ((epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0) ? nts * 256 : 0);
       int left = budget - wbytes - resb;
       int outb = 0;
@@ -1317,15 +1343,15 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       const int ra = left / ubytes;
       if (ra >= 2) { best_slices = sl; best_nt = nts; best_ra = ra > 6 ? 6 : ra; best_res = resb; best_out = outb; best_wst = wst; }
     }
-    const long long clusters_max = (g_num_sms / 2) / (best_slices ? best_slices : 1);
+    const long long clusters_max = (g_num_sms / 2) / (groups * (best_slices ? best_slices : 1));
     const bool worth = best_slices && clusters_max >= 1 && n_pairs >= 3 * clusters_max && p.kb_per_src <= 3;
-    if (best_slices && clusters_max >= 1 && (variant == 13 || worth)) {
+    if (best_slices && clusters_max >= 1 && nboxes <= 28 && (variant == 13 || worth)) {       // 28 weight-box barriers in the kernel
       if (reinterpret_cast<uintptr_t>(x) & 15) return VMGB_EINVAL;
       p.nt_per_g = best_slices; p.NT = best_nt; p.b_stage_bytes = (best_nt / 2) * 128; p.ra = best_ra; p.out_smem = best_out;
       p.wst = best_wst; p.res_smem = best_wst ? 0 : best_res;
       p.BH = 16; p.BW = 8; p.a_unit_bytes = ubytes; p.stages = 0;
       p.tiles_h = (H + 15) / 16; p.tiles_w = (W + 7) / 8;
-      p.total_tiles = n_mt * p.nt_per_g;
+      p.total_tiles = n_mt * groups * p.nt_per_g;
       CUtensorMap mA, mB;
       {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
@@ -1334,7 +1360,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
         if (!encode_bf16(&mA, x, 4, dims, str, box)) return VMGB_EINVAL;
       }
       {
-        cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)9 * Cout_g};
+        cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)groups * 9 * Cout_g};
         cuuint64_t str[1] = {(cuuint64_t)Kp * 2};
         cuuint32_t box[2] = {64, (cuuint32_t)(p.NT / 2)};
         if (!encode_bf16(&mB, w, 2, dims, str, box)) return VMGB_EINVAL;
@@ -1342,10 +1368,11 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       long long per = n_pairs < clusters_max ? n_pairs : clusters_max;
       const int smem = p.ra * p.a_unit_bytes + (nboxes * p.b_stage_bytes + 1023) / 1024 * 1024 + 1024 + 512 + 1024 + best_res + p.out_smem;
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)(2 * per * best_slices)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
-      cudaLaunchAttribute at[1];
+      cfg.gridDim = dim3((unsigned)(2 * per * groups * best_slices)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
+      cudaLaunchAttribute at[2];
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
+      at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
       cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel, mA, mB, p);
       if (e != cudaSuccess) { g_last_cuda_error = (int)e; return VMGB_ECUDA; }
       return check_launch();
