@@ -9,7 +9,7 @@ GPU (torchrun), one clip per rank, no data-path collective (clips are independen
 
 Reported on ONE JSON line: `value` = 720p output frames/s with inputs resident in HBM (CUDA events,
 max over ranks); `e2e` = same through the public nn.Module call with pinned-host input and output copies
-inside the timed region; `roofline` = tensor-pipe fraction of the dominant kernel (conv_tc_kernel) from
+inside the timed region; `roofline` = tensor-pipe fraction of the dominant kernel (the trajectory resblock 3x3 conv, conv3x3_ws2_kernel) from
 per-launch CUDA events in one extra instrumented forward; `cpu_baseline` = the CPU oracle
 (oracle/vmg_oracle.py, a port of the reference forward) on a bounded sample, rank 0, N=1 only.
 `--impl reference` times that CPU oracle as the reference arm (the reference is pure PyTorch; its
@@ -234,9 +234,9 @@ def main():
             s.record()
             rc = real(*a)
             e.record()
-            # C prototype positions 17..24 = n_img,H,W,Cin,Cout,R,S,groups
+            # C prototype positions 17..24 = n_img,H,W,Cin,Cout,R,S,groups ; 25/27 = act / epilogue
             n_img, h, w, cin, cout, r, s_, g = a[17:25]
-            recs.append((s, e, 2.0 * n_img * h * w * cout * r * s_ * (cin // g)))
+            recs.append((s, e, 2.0 * n_img * h * w * cout * r * s_ * (cin // g), (n_img, h, w, cin, cout, r, g, a[28])))
             return rc
         ops.lib().vmgb_conv2d_nhwc_tc = timed
         use_graph = model.use_cuda_graph
@@ -252,15 +252,48 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
+        # the dominant kernel is timed inside a long step (thousands of back-to-back launches): sustained figure
         peak = peaks.get('bf16_tflops_sustained', 1400.0)
         src = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if 'bf16_tflops_sustained' in peaks else 'fallback 1.4 PFLOP/s sustained (of fallback)'
         if recs:
-            tot_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
-            tot_fl = sum(f for _, _, f in recs)
-            ach = tot_fl / (tot_ms * 1e-3) / 1e12
-            roofline = {'kernel': 'conv_tc_kernel', 'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                        'traffic': None, 'launches': len(recs), 'kernel_ms_per_step': tot_ms, 'share_of_step': tot_ms / ms_step,
-                        'algorithmic_tflop_per_step': tot_fl / 1e12, 'peak_source': src}
+            # group the tcgen05 convolution launches by shape; the dominant kernel = the group with the most device time
+            groups = {}
+            for s, e, fl, key in recs:
+                gr = groups.setdefault(key, [0, 0.0, 0.0])
+                gr[0] += 1
+                gr[1] += s.elapsed_time(e)
+                gr[2] += fl
+            all_ms = sum(v[1] for v in groups.values())
+            all_fl = sum(v[2] for v in groups.values())
+            # the two epilogue flavours of the trajectory resblock conv (conv1: ReLU store, conv2: residual add) are one kernel
+            by_shape = {}
+            for key, v in groups.items():
+                b = by_shape.setdefault(key[:7], [0, 0.0, 0.0, 0.0])
+                b[0] += v[0]; b[1] += v[1]; b[2] += v[2]
+                ni, hh, ww, ci, co, rr, gg, ep = key      # bf16 activations in + out (+ residual) and the weights, once per launch
+                b[3] += v[0] * (2.0 * ni * hh * ww * (ci + co + (co if ep else 0)) + 2.0 * rr * rr * (ci // gg) * co)
+            dom_key, dom = max(by_shape.items(), key=lambda kv: kv[1][1])
+            ach = dom[2] / (dom[1] * 1e-3) / 1e12
+            n_img, h, w, cin, cout, r, g = dom_key
+            traffic, traffic_src = None, None
+            try:                                  # dram bytes per launch of the same shape from the committed ncu capture
+                cap = json.load(open(os.path.join(ROOT, 'profiles', 'r1_dominant_kernel_ncu.json')))
+                if cap.get('shape') == [n_img, h, w, cin, cout, r, g]:
+                    traffic = cap['dram_bytes_read'] + cap['dram_bytes_write']
+                    traffic_src = 'profiles/r1_dominant_kernel_ncu.json'
+            except Exception:
+                pass
+            kname = 'conv3x3_ws2_kernel' if (r == 3 and cin // g <= 192) else 'conv_tc_kernel'
+            roofline = {'kernel': kname, 'shape': {'n_img': n_img, 'H': h, 'W': w, 'Cin': cin, 'Cout': cout, 'R': r, 'groups': g},
+                        'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                        'traffic': traffic, 'traffic_source': traffic_src,
+                        'algorithmic_bytes_per_launch': dom[3] / dom[0],
+                        'launches': dom[0], 'us_per_launch': 1e3 * dom[1] / dom[0], 'kernel_ms_per_step': dom[1],
+                        'share_of_step': dom[1] / ms_step, 'algorithmic_tflop_per_launch': dom[2] / dom[0] / 1e12,
+                        'all_tcgen05_convs': {'launches': len(recs), 'ms_per_step': all_ms, 'achieved': all_fl / (all_ms * 1e-3) / 1e12,
+                                              'share_of_step': all_ms / ms_step},
+                        'timing': 'CUDA events around every launch of one eager forward (graphs off) on the launching stream',
+                        'peak_source': src}
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
