@@ -77,7 +77,12 @@ int vmgb_conv2d_nhwc(const void* x, const void* x1, const void* x2, int n_src, i
 
 /* ---- conv2d / linear, tcgen05 + TMEM + TMA path (bf16 operands, fp32 accumulate) -----------
  * Same contract as vmgb_conv2d_nhwc; x must be bf16 with x_pitch % 8 == 0; w is bf16 packed
- * [groups][R*S][Cout/groups][Kp], Kp = roundup(Cin/groups, 16) zero padded (see vmgb_pack_weight_tc). */
+ * [groups][R*S][Cout/groups][Kp], Kp = roundup(Cin/groups, 16) zero padded (see vmgb_pack_weight_tc).
+ * variant: 0 = automatic kernel choice (what the model uses); the others force one kernel for tests and
+ * tools/microbench.py and return VMGB_EUNSUPPORTED (-2) when that kernel does not take the shape:
+ *   1 = per-tap ring kernel; 8 / 9 = single-CTA weight-stationary kernel (column-shifted / wide activation units,
+ *   R = 3 or 7); 13 = weight-stationary kernel on a CTA pair (cta_group::2, R = 3, one source);
+ *   13 + 32*d = the same with bottleneck-probe flags d (tools only, results are NOT valid). */
 int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2, int n_src, int x_pitch,
                         const void* w, int Kp, const void* bias,
                         void* out, int out_dt, int out_pitch,

@@ -41,6 +41,7 @@ def conv_cases():
         ('traj_res_112_b2', 2, 184, 320, 112, 112, 3, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
         ('traj_res_112_b4', 4, 184, 320, 112, 112, 3, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
         ('traj_res_112_b4_store', 4, 184, 320, 112, 112, 3, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
+        ('tiny_1round_112', 1, 64, 296, 112, 112, 3, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
         ('ffn_fc1_g4_112', 25, 184, 320, 112, 672, 3, 4, 1, ops.EPI_STORE, ops.ACT_GELU, 0),
         ('ffn_fc2_672to112', 1, 1, 25 * 184 * 320, 672, 112, 1, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
         ('linear_112', 1, 1, 25 * 184 * 320, 112, 112, 1, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
