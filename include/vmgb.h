@@ -109,11 +109,13 @@ int vmgb_layernorm(const void* x, int x_dt, void* out, int out_dt, const void* g
 int vmgb_morph_permute(const void* src, int src_dt, void* dst, int dst_dt,
                        int BT, int H, int W, int C, int chunk, int axis, int inverse, int a_pitch, void* stream);
 
-/* ---- grouped channel sums (fp32 out, must be zeroed by the caller).  function.py:791 (TAB global
+/* ---- grouped channel sums (fp32 out; acc = groups*C 64-bit integers of scratch, ZEROED by the caller: the
+ * partial sums are accumulated in 2^-24 fixed point so that the result is independent of the order of the
+ * atomics, i.e. bit-identical from run to run).  function.py:791 (TAB global
  * mean over T,H,W per sample), :546-558 (CALayer per-frame pool).  Rows are laid out as
  * [n_seg][groups][seg_rows]: out[g][c] = scale * sum_{s,r} (a+b+c)[(s*groups + g)*seg_rows + r][c].
  * (frames are stored time-major [T,B,...]: per-sample sums use n_seg=T, groups=B, seg_rows=H*W.) */
-int vmgb_channel_sum(const void* a, const void* b, const void* c, int dt, float* out,
+int vmgb_channel_sum(const void* a, const void* b, const void* c, int dt, float* out, long long* acc,
                      int n_seg, int groups, long long seg_rows, int C, float scale, void* stream);
 
 /* softmax over the 3 branch weights: logits fp32 [B][3C] with feature index 3*c+j (function.py:792)
@@ -180,9 +182,10 @@ int vmgb_resample_ln(const void* x, const void* add, int dt, void* out, int out_
 
 /* ---- mdsc shortcut pieces (vmg.py:389-400,519,525) */
 int vmgb_maxpool4(const void* x, int dt, void* out, int out_dt, int BT, int H, int W, int C, void* stream);
-/* per-frame GroupNorm(1,C)+ReLU given per-frame sums: stats fp32 [frames][2] = (sum, sum of squares) */
-int vmgb_frame_stats(const void* x, int dt, float* stats, int frames, long long elems_per_frame, void* stream);
-int vmgb_groupnorm1_relu(const void* x, int dt, const float* stats, const void* gamma, const void* beta, void* out, int out_dt,
+/* per-frame GroupNorm(1,C)+ReLU given per-frame sums: stats = 64-bit integers [frames][2] = (sum, sum of squares) in
+ * 2^-20 fixed point (order-independent atomics), ZEROED by the caller before vmgb_frame_stats */
+int vmgb_frame_stats(const void* x, int dt, long long* stats, int frames, long long elems_per_frame, void* stream);
+int vmgb_groupnorm1_relu(const void* x, int dt, const long long* stats, const void* gamma, const void* beta, void* out, int out_dt,
                          int frames, long long rows_per_frame, int C, float eps, void* stream);
 
 /* ---- SPyNet helpers (vmg.py:39-123) : all fp32 channels-last ----------------------------------

@@ -132,6 +132,18 @@ def test_conv_tcgen05_many_tiles_persistent():
     close(out, ref, 2e-3)
 
 
+def test_reductions_are_run_to_run_identical():
+    # many blocks accumulate into the same output: the fixed-point atomics must make the result independent of their order
+    x = rnd(4, 96, 128, 112, seed=31).bfloat16().to(DEV)
+    g, b = rnd(112, seed=32).to(DEV), rnd(112, seed=33).to(DEV)
+    s0 = ops.channel_sum(x, x, None, 2, 2, 96 * 128, 1.0 / (2 * 96 * 128))
+    n0 = ops.groupnorm1_relu(x, g, b)
+    for _ in range(5):
+        assert torch.equal(ops.channel_sum(x, x, None, 2, 2, 96 * 128, 1.0 / (2 * 96 * 128)), s0)
+        assert torch.equal(ops.groupnorm1_relu(x, g, b), n0)
+    close(s0, emu.channel_sum(x.cpu(), x.cpu(), None, 2, 2, 96 * 128, 1.0 / (2 * 96 * 128)), 1e-5)
+
+
 @pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)], ids=['f32', 'bf16'])
 def test_row_kernels(dtype, tol):
     x = rnd(5, 13, 144, seed=1).to(dtype)

@@ -171,16 +171,18 @@ template <int ROWS>
 __global__ void __launch_bounds__(256) layernorm_half_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              long long rows, int C, float eps) {
-  const int hl = threadIdx.x & 15;
-  const long long hw_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-  const long long n_hw = ((long long)gridDim.x * blockDim.x) >> 4;
+  const int hl = threadIdx.x & 15, hsel = (threadIdx.x >> 4) & 1;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int c = 8 * hl;
   const bool act = c < C;
   float g[8], b[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { g[k] = act ? gamma[c + k] : 0.f; b[k] = act ? beta[c + k] : 0.f; }
   const float inv_c = 1.f / (float)C;
-  for (long long r0 = hw_id * ROWS; r0 < rows; r0 += n_hw * ROWS) {
+  // the loop bound is uniform over the warp (both half-warps take part in every full-mask shuffle)
+  for (long long w0 = warp_id * 2 * ROWS; w0 < rows; w0 += n_warps * 2 * ROWS) {
+    const long long r0 = w0 + hsel * ROWS;
     uint4 raw[ROWS];
 #pragma unroll
     for (int k = 0; k < ROWS; ++k)
@@ -430,8 +432,12 @@ __global__ void __launch_bounds__(32 * MORPH_WARPS) morph_block16_kernel(const _
 // grouped channel sums (atomic accumulation of per-block partials into a zeroed fp32 buffer)
 // grid = (row chunks, groups); block = 256 threads = 8 row lanes x 32 channel lanes
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) channel_sum_kernel(const void* a, const void* b, const void* c, int dt, float* out,
-                                                          int n_groups, long long rows_per_group, int C, float scale, int rows_per_block) {
+// Partials are accumulated as 2^-24 fixed point in 64-bit integers: integer addition is associative, so the result does
+// not depend on the order in which the blocks' atomics land (float atomics made the whole forward differ in the last
+// bits from run to run).
+constexpr float CSUM_FIX = 16777216.f;
+__global__ void __launch_bounds__(256) channel_sum_kernel(const void* a, const void* b, const void* c, int dt, unsigned long long* acc,
+                                                          int n_groups, long long rows_per_group, int C, int rows_per_block) {
   __shared__ float part[8][33];
   // blockIdx.y = segment*n_groups + group ; rows_per_group here = rows of ONE segment
   const int g = blockIdx.y % n_groups;
@@ -457,10 +463,15 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const void* a, const v
       float tot = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) tot += part[k][cl];
-      atomicAdd(out + (long long)g * C + ch, tot * scale);
+      atomicAdd(acc + (long long)g * C + ch, (unsigned long long)__float2ll_rn(tot * CSUM_FIX));
     }
     __syncthreads();
   }
+}
+
+__global__ void channel_sum_finalize_kernel(const unsigned long long* __restrict__ acc, float* __restrict__ out, int n, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)((double)(long long)acc[i] * (1.0 / 16777216.0) * (double)scale);
 }
 
 __global__ void softmax3_kernel(const float* __restrict__ logits, float* __restrict__ a, int B, int C) {
@@ -635,7 +646,8 @@ __global__ void maxpool4_kernel(const void* x, int dt, void* out, int out_dt, in
 }
 
 // per-frame (sum, sum of squares) -> stats[frame][2]; grid = (chunks, frames)
-__global__ void __launch_bounds__(256) frame_stats_kernel(const void* x, int dt, float* stats, long long elems, int elems_per_block) {
+// (2^-20 fixed point in 64-bit integers, see channel_sum_kernel: order-independent, hence run-to-run identical)
+__global__ void __launch_bounds__(256) frame_stats_kernel(const void* x, int dt, unsigned long long* stats, long long elems, int elems_per_block) {
   __shared__ float sh[2][8];
   const int fr = blockIdx.y;
   const long long e0 = (long long)blockIdx.x * elems_per_block, e1 = min(elems, e0 + elems_per_block);
@@ -647,20 +659,20 @@ __global__ void __launch_bounds__(256) frame_stats_kernel(const void* x, int dt,
   if (threadIdx.x == 0) {
     float ts = 0.f, tq = 0.f;
     for (int k = 0; k < 8; ++k) { ts += sh[0][k]; tq += sh[1][k]; }
-    atomicAdd(stats + 2 * fr, ts);
-    atomicAdd(stats + 2 * fr + 1, tq);
+    atomicAdd(stats + 2 * fr, (unsigned long long)__float2ll_rn(ts * 1048576.f));
+    atomicAdd(stats + 2 * fr + 1, (unsigned long long)__float2ll_rn(tq * 1048576.f));
   }
 }
 
-__global__ void groupnorm1_relu_kernel(const void* x, int dt, const float* __restrict__ stats, const float* __restrict__ gamma,
+__global__ void groupnorm1_relu_kernel(const void* x, int dt, const long long* __restrict__ stats, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, void* out, int out_dt, long long rows_per_frame, int C,
                                        float eps, long long total) {
   const float cnt = (float)(rows_per_frame * C);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const long long fr = (i / C) / rows_per_frame;
-    const float mean = stats[2 * fr] / cnt;
-    const float var = fmaxf(stats[2 * fr + 1] / cnt - mean * mean, 0.f);
+    const float mean = (float)((double)stats[2 * fr] * (1.0 / 1048576.0)) / cnt;
+    const float var = fmaxf((float)((double)stats[2 * fr + 1] * (1.0 / 1048576.0)) / cnt - mean * mean, 0.f);
     const float v = (ldf(x, dt, i) - mean) * rsqrtf(var + eps) * gamma[c] + beta[c];
     stf(out, out_dt, i, fmaxf(v, 0.f));
   }
@@ -749,15 +761,16 @@ extern "C" int vmgb_morph_permute(const void* src, int src_dt, void* dst, int ds
   return check_launch();
 }
 
-extern "C" int vmgb_channel_sum(const void* a, const void* b, const void* c, int dt, float* out, int n_seg, int groups,
+extern "C" int vmgb_channel_sum(const void* a, const void* b, const void* c, int dt, float* out, long long* acc, int n_seg, int groups,
                                 long long seg_rows, int C, float scale, void* stream) {
-  if (!a || !out || !dt_ok(dt) || groups <= 0 || n_seg <= 0 || seg_rows <= 0 || C <= 0) return VMGB_EINVAL;
+  if (!a || !out || !acc || !dt_ok(dt) || groups <= 0 || n_seg <= 0 || seg_rows <= 0 || C <= 0) return VMGB_EINVAL;
   if ((long long)n_seg * groups > 65535) return VMGB_EINVAL;
   int rpb = 256;
   long long chunks = (seg_rows + rpb - 1) / rpb;
   while (chunks * groups * n_seg > 148LL * 32 && rpb < (1 << 20)) { rpb *= 2; chunks = (seg_rows + rpb - 1) / rpb; }
   dim3 grid((unsigned)chunks, n_seg * groups);
-  channel_sum_kernel<<<grid, 256, 0, as_stream(stream)>>>(a, b, c, dt, out, groups, seg_rows, C, scale, rpb);
+  channel_sum_kernel<<<grid, 256, 0, as_stream(stream)>>>(a, b, c, dt, (unsigned long long*)acc, groups, seg_rows, C, rpb);
+  channel_sum_finalize_kernel<<<(groups * C + 255) / 256, 256, 0, as_stream(stream)>>>((const unsigned long long*)acc, out, groups * C, scale);
   return check_launch();
 }
 
@@ -844,15 +857,15 @@ extern "C" int vmgb_maxpool4(const void* x, int dt, void* out, int out_dt, int B
   return check_launch();
 }
 
-extern "C" int vmgb_frame_stats(const void* x, int dt, float* stats, int frames, long long elems_per_frame, void* stream) {
+extern "C" int vmgb_frame_stats(const void* x, int dt, long long* stats, int frames, long long elems_per_frame, void* stream) {
   if (!x || !stats || !dt_ok(dt) || frames <= 0 || elems_per_frame <= 0) return VMGB_EINVAL;
   int epb = 8192;
   dim3 grid((unsigned)((elems_per_frame + epb - 1) / epb), frames);
-  frame_stats_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, dt, stats, elems_per_frame, epb);
+  frame_stats_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, dt, (unsigned long long*)stats, elems_per_frame, epb);
   return check_launch();
 }
 
-extern "C" int vmgb_groupnorm1_relu(const void* x, int dt, const float* stats, const void* gamma, const void* beta, void* out,
+extern "C" int vmgb_groupnorm1_relu(const void* x, int dt, const long long* stats, const void* gamma, const void* beta, void* out,
                                     int out_dt, int frames, long long rows_per_frame, int C, float eps, void* stream) {
   if (!x || !stats || !gamma || !beta || !out || !dt_ok(dt) || !dt_ok(out_dt)) return VMGB_EINVAL;
   long long total = (long long)frames * rows_per_frame * C;

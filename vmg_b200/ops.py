@@ -24,7 +24,7 @@ EPI_STORE, EPI_RESADD, EPI_GATE = 0, 1, 2
 _CTYPES = {
     'int': ctypes.c_int, 'float': ctypes.c_float, 'long long': ctypes.c_longlong,
     'void*': ctypes.c_void_p, 'const void*': ctypes.c_void_p, 'float*': ctypes.c_void_p,
-    'const float*': ctypes.c_void_p, 'const char*': ctypes.c_char_p, 'void': None,
+    'const float*': ctypes.c_void_p, 'long long*': ctypes.c_void_p, 'const long long*': ctypes.c_void_p, 'const char*': ctypes.c_char_p, 'void': None,
 }
 
 
@@ -283,8 +283,9 @@ def channel_sum(a, b, c, n_seg, groups, seg_rows, scale):
     C = a.shape[-1]
     for t in (a, b, c):
         assert t is None or (t.is_contiguous() and t.dtype == a.dtype)
-    out = torch.zeros((groups, C), device=a.device, dtype=torch.float32)
-    _ck(lib().vmgb_channel_sum(a.data_ptr(), _ptr(b), _ptr(c), _dt(a), out.data_ptr(), n_seg, groups, seg_rows, C,
+    out = torch.empty((groups, C), device=a.device, dtype=torch.float32)
+    acc = torch.zeros((groups, C), device=a.device, dtype=torch.int64)        # fixed-point accumulators (order-independent atomics)
+    _ck(lib().vmgb_channel_sum(a.data_ptr(), _ptr(b), _ptr(c), _dt(a), out.data_ptr(), acc.data_ptr(), n_seg, groups, seg_rows, C,
                                scale, _stream()), 'vmgb_channel_sum')
     return out
 
@@ -381,7 +382,7 @@ def groupnorm1_relu(x, gamma, beta, eps=1e-5):
     """GroupNorm(1, C) per frame followed by ReLU; x [N,H,W,C]."""
     require_device()
     N, H, W, C = x.shape
-    stats = torch.zeros((N, 2), device=x.device, dtype=torch.float32)
+    stats = torch.zeros((N, 2), device=x.device, dtype=torch.int64)          # fixed-point (sum, sum of squares) per frame
     _ck(lib().vmgb_frame_stats(x.data_ptr(), _dt(x), stats.data_ptr(), N, H * W * C, _stream()), 'vmgb_frame_stats')
     out = torch.empty_like(x)
     _ck(lib().vmgb_groupnorm1_relu(x.data_ptr(), _dt(x), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
