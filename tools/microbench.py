@@ -45,6 +45,7 @@ def conv_cases():
         ('ffn_fc1_g4_112', 25, 184, 320, 112, 672, 3, 4, 1, ops.EPI_STORE, ops.ACT_GELU, 0),
         ('ffn_fc2_672to112', 1, 1, 25 * 184 * 320, 672, 112, 1, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
         ('linear_112', 1, 1, 25 * 184 * 320, 112, 112, 1, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
+        ('gate_proj_112', 1, 1, 25 * 184 * 320, 112, 112, 1, 1, 1, ops.EPI_GATE, ops.ACT_NONE, 0),
         ('linear_448', 1, 1, 100 * 23 * 40, 448, 448, 1, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
         ('upconv2_112to256_ps', 4, 360, 640, 112, 256, 3, 1, 1, ops.EPI_STORE, ops.ACT_LRELU, 2),
         ('hrconv_64', 2, 720, 1280, 64, 64, 3, 1, 1, ops.EPI_STORE, ops.ACT_LRELU, 0),
@@ -71,14 +72,15 @@ def run_conv(iters, only=None, variants=(0,)):
         oshape = (N, 2 * H, 2 * W, Cout // 4) if ps else (N, H, W, Cout)
         o = torch.empty(oshape, device=DEV, dtype=torch.float32 if Cout == 3 else torch.bfloat16)
         res = torch.randn(oshape, device=DEV).bfloat16() if epi != ops.EPI_STORE else None
+        aux = torch.randn(oshape, device=DEV).bfloat16() if epi == ops.EPI_GATE else None
         ref = None
         if len(variants) > 1:            # cross-check every variant against the per-tap kernel
-            ops.conv2d(xs if n_src > 1 else xs[0], pc, act=act, alpha=0.1, epi=epi, res=res, res_scale=0.1, pixel_shuffle=ps, out=o, tc_variant=1)
+            ops.conv2d(xs if n_src > 1 else xs[0], pc, act=act, alpha=0.1, epi=epi, res=res, aux=aux, res_scale=0.1, pixel_shuffle=ps, out=o, tc_variant=1)
             ref = o.float().clone()
         for variant in variants:
             if (1 < variant < 8 and R != 3) or (variant == 8 and R not in (3, 7)) or (variant > 8 and R != 3):
                 continue
-            fn = lambda: ops.conv2d(xs if n_src > 1 else xs[0], pc, act=act, alpha=0.1, epi=epi, res=res, res_scale=0.1, pixel_shuffle=ps, out=o, tc_variant=variant)
+            fn = lambda: ops.conv2d(xs if n_src > 1 else xs[0], pc, act=act, alpha=0.1, epi=epi, res=res, aux=aux, res_scale=0.1, pixel_shuffle=ps, out=o, tc_variant=variant)
             try:
                 ms = timeit(fn, iters, flush)
             except RuntimeError as e:

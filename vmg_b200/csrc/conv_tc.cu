@@ -586,7 +586,9 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
   const int c_lo = half ? (nchunks + 1) >> 1 : 0, c_hi = half ? nchunks : (nchunks + 1) >> 1;
   const int epi = EPI < 0 ? p.epi : EPI;
   const bool has_res = epi != VMGB_EPI_STORE;          // host: bf16 residual, 16-byte aligned rows, NT <= 128 (one pass per warp)
+  const bool has_aux = epi == VMGB_EPI_GATE;           // gate operand: a second buffer per warp, same layout, same pitch rules
   const uint32_t buf = smem_u32(bias_s) + 1024 + (uint32_t)ew * 4096u;
+  const __nv_bfloat16* auxp = reinterpret_cast<const __nv_bfloat16*>(p.aux);
   const int bw_shift = 31 - __clz(p.BW), bw_mask = p.BW - 1;
   const int crow0 = lane >> 3, piece = lane & 7;
   const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(p.res);
@@ -611,6 +613,10 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
         const __nv_bfloat16* rp = rp0 + (pbase + (long long)dh * p.W + dw) * p.res_pitch;
         const uint32_t dst = buf + (uint32_t)r * 128u + (uint32_t)((piece ^ (r & 7)) << 4);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rp) : "memory");
+        if (has_aux) {
+          const __nv_bfloat16* ap = auxp + g * p.Cout_g + nt * p.NT + col + (pbase + (long long)dh * p.W + dw) * p.aux_pitch;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 8u * 4096u), "l"(ap) : "memory");
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -653,13 +659,17 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
       const int chn = min(4, c_hi - ch0);
       auto process = [&](int c, const uint32_t* raw) {
         const uint32_t c0 = rowbase + (((uint32_t)(2 * c) ^ sw) << 4), c1 = rowbase + (((uint32_t)(2 * c + 1) ^ sw) << 4);
-        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, a0 = r0, a1 = r0;
         const bool hp = has_res && pvalid && nt * p.NT + (ch0 + c) * 16 + 16 <= p.Cout_g;
         if (hp) {
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(c0) : "memory");
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(c1) : "memory");
+          if (has_aux) {
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a0.x), "=r"(a0.y), "=r"(a0.z), "=r"(a0.w) : "r"(c0 + 8u * 4096u) : "memory");
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a1.x), "=r"(a1.y), "=r"(a1.z), "=r"(a1.w) : "r"(c1 + 8u * 4096u) : "memory");
+          }
         }
-        epilogue_chunk<ACT, EPI, 0>(p, raw, pvalid, img, hh, ww, pix, g, nt, ch0 + c, bias_s, hp, r0, r1, c0, c1);
+        epilogue_chunk<ACT, EPI, 0>(p, raw, pvalid, img, hh, ww, pix, g, nt, ch0 + c, bias_s, hp, r0, r1, c0, c1, hp && has_aux, a0, a1);
       };
       uint32_t rawA[16], rawB[16];
       __syncwarp();
@@ -715,6 +725,7 @@ __device__ __forceinline__ void run_epilogue_w(const TcP& p, float* bias_s, uint
     return;                                                                                                              \
   }
   VMGB_EPIW_CASE(VMGB_ACT_NONE, VMGB_EPI_RESADD)
+  VMGB_EPIW_CASE(VMGB_ACT_NONE, VMGB_EPI_GATE)
   VMGB_EPIW_CASE(VMGB_ACT_RELU, VMGB_EPI_STORE)
   VMGB_EPIW_CASE(VMGB_ACT_LRELU, VMGB_EPI_STORE)
   VMGB_EPIW_CASE(VMGB_ACT_GELU, VMGB_EPI_STORE)
@@ -1062,20 +1073,23 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 // Work split: cluster c owns combo = c % slices and walks the tile PAIRS c / slices, + clusters / slices, ...
 // (tile 2t -> rank 0, tile 2t+1 -> rank 1; an odd tail tile is loaded fully out of bounds = zeros).
 // ---------------------------------------------------------------------------------------------
+constexpr int WS2_MAX_BOXES = 36;      // weight-box barriers: 9 taps x up to 4 K blocks
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcP p) {
+conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB, const TcP p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr int RR = 3, BWX = 10, TAPS = 9, UROWS = 18;
   // weights: one SWIZZLE_128B box {64 k, N/2 rows} per (K block, tap).  (A dense SWIZZLE_32B layout, one {16 k, N/2}
   // box per K = 16 slice, saves 16 KB at C = 112 but measured ~25 % slower MMA issue on B200.)
-  const int nboxes = p.kb_per_src * TAPS;
+  const int nkb = p.n_src * p.kb_per_src;              // K blocks of one tile: (source of the virtual concat, 64-channel block)
+  const int nboxes = nkb * TAPS;
   const uint32_t a_base = smem_base;
   const uint32_t w_base = a_base + p.ra * p.a_unit_bytes;
   const uint32_t bar_base = (w_base + nboxes * p.b_stage_bytes + 1023u) & ~1023u;
   const uint32_t afull0 = bar_base, aempty0 = afull0 + 8 * p.ra;
-  const uint32_t wfull0 = aempty0 + 8 * p.ra;          // one barrier per weight box (<= 27): the first tile starts on tap 0's weights
-  const uint32_t tfull0 = wfull0 + 8 * 28, tempty0 = tfull0 + 16;
+  const uint32_t wfull0 = aempty0 + 8 * p.ra;          // one barrier per weight box (<= 36): the first tile starts on tap 0's weights
+  const uint32_t tfull0 = wfull0 + 8 * WS2_MAX_BOXES, tempty0 = tfull0 + 16;
   const uint32_t tmem_slot = tempty0 + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -1087,7 +1101,7 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     for (int i = 0; i < nboxes; ++i) mbar_init(wfull0 + 8 * i, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 512); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
   }
   if (warp == 2) {
@@ -1105,7 +1119,7 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   const long long cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   const int combo = (int)(cl % ncombo);
   const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
-  const int koff = (g * p.Cin_g) & 7;                 // grouped conv: the channel box starts 16-byte aligned, the packed weights are shifted alike
+  const int koff = p.n_src > 1 ? 0 : (g * p.Cin_g) & 7;      // grouped conv: the channel box starts 16-byte aligned, the packed weights are shifted alike
   const long long first = cl / ncombo, step = ncl / ncombo;
   const long long n_mt = (long long)p.n_img * tiles_per_img;
   const long long n_pairs = (n_mt + 1) >> 1;
@@ -1115,11 +1129,12 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     // ===================== TMA producer (both CTAs) =====================
     const uint32_t wfull0_l = mapa_rank(wfull0, 0), afull0_l = mapa_rank(afull0, 0);
     if (elect_one()) {                 // this CTA's half of the weight slice, once, in the order the MMAs consume it
-      for (int kb = 0; kb < p.kb_per_src; ++kb)
+      for (int kbt = 0; kbt < nkb; ++kbt)
         for (int tap = 0; tap < TAPS; ++tap) {
-          const int box = kb * TAPS + tap;
+          const int box = kbt * TAPS + tap;
+          const int src = kbt / p.kb_per_src, kb = kbt - src * p.kb_per_src;
           if (rank == 0) mbar_expect_tx(wfull0 + 8 * box, (uint32_t)(2 * NH * 128));
-          tma_load_2d_2sm(w_base + box * p.b_stage_bytes, &mapB, wfull0_l + 8 * box, kb * 64,
+          tma_load_2d_2sm(w_base + box * p.b_stage_bytes, &mapB, wfull0_l + 8 * box, src * p.Cs + kb * 64,
                           (g * TAPS + tap) * p.Cout_g + nt * p.NT + (int)rank * NH);
         }
     }
@@ -1134,13 +1149,16 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
         h0 = (rem / p.tiles_w) * 16; w0 = (rem % p.tiles_w) * 8;
       }
-      for (int kb = 0; kb < p.kb_per_src; ++kb) {
+      for (int kbt = 0; kbt < nkb; ++kbt) {
+        const int src = kbt / p.kb_per_src, kb = kbt - src * p.kb_per_src;
+        const CUtensorMap* mA = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
+        const int ca = (p.n_src > 1 ? 0 : ((g * p.Cin_g) & ~7)) + kb * 64;
         mbar_wait(aempty0 + 8 * ia, pa ^ 1);
         if (elect_one()) {
           if (p.dbg & 4) { if (rank == 0) mbar_arrive(afull0 + 8 * ia); }
           else {
             if (rank == 0) mbar_expect_tx(afull0 + 8 * ia, 2 * a_bytes);
-            tma_load_4d_2sm(a_base + ia * p.a_unit_bytes, &mapA, afull0_l + 8 * ia, ((g * p.Cin_g) & ~7) + kb * 64, w0 - 1, h0 - 1, img);
+            tma_load_4d_2sm(a_base + ia * p.a_unit_bytes, mA, afull0_l + 8 * ia, ca, w0 - 1, h0 - 1, img);
           }
         }
         __syncwarp();
@@ -1162,7 +1180,8 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
       uint32_t accumulate = 0;
-      for (int kb = 0; kb < p.kb_per_src; ++kb) {
+      for (int kbt = 0; kbt < nkb; ++kbt) {
+        const int kb = kbt % p.kb_per_src;
         const int nks = min(4, (p.Cs + koff - kb * 64 + 15) >> 4);
         mbar_wait(afull0 + 8 * ia, pa);
         tc_fence_after();
@@ -1170,15 +1189,15 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         if (!(p.dbg & 1)) {
 #pragma unroll
           for (int tap = 0; tap < TAPS; ++tap) {
-            if (it == 0) { mbar_wait(wfull0 + 8 * (kb * TAPS + tap), 0); tc_fence_after(); }     // weights of this box have landed (first tile only)
+            if (it == 0) { mbar_wait(wfull0 + 8 * (kbt * TAPS + tap), 0); tc_fence_after(); }     // weights of this box have landed (first tile only)
             const uint64_t ad = smem_desc_sw128_sbo(a_unit + (uint32_t)((tap / RR) * BWX + (tap % RR)) * 128u, (uint32_t)BWX * 128u);
-            const uint64_t bd = smem_desc_sw128(w_base + (kb * TAPS + tap) * p.b_stage_bytes);
+            const uint64_t bd = smem_desc_sw128(w_base + (kbt * TAPS + tap) * p.b_stage_bytes);
             for (int ks = 0; ks < nks; ++ks)
               umma_f16_2sm_if(issue, d_tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)((tap | ks) > 0));
           }
         }
         umma_commit_2sm_if(issue, aempty0 + 8 * ia, (uint16_t)3);
-        if (kb == p.kb_per_src - 1) umma_commit_2sm_if(issue, tfull0 + 8 * as, (uint16_t)3);
+        if (kbt == nkb - 1) umma_commit_2sm_if(issue, tfull0 + 8 * as, (uint16_t)3);
         __syncwarp();
         accumulate = 1;
         if (++ia == p.ra) { ia = 0; pa ^= 1; }
@@ -1232,6 +1251,8 @@ static int g_num_sms = 0;
 static int g_smem_optin = 0;
 static std::once_flag g_once;
 static int g_pdl = 1;         // VMGB_PDL=0 turns programmatic dependent launch off
+static int g_ws2_multi = 1;   // VMGB_WS2_MULTI=0: multi-source convs stay on the per-tap kernel (A/B switch)
+static int g_wst_gate = 1;    // VMGB_WST_GATE=0: gate epilogue on the per-thread staging path (A/B switch)
 static int g_no_wst = 0;      // VMGB_NO_WST=1: A/B switch (tools/microbench.py) for the warp-private staging epilogue
 
 static void tc_init() {
@@ -1240,7 +1261,9 @@ static void tc_init() {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
     g_encode = (EncodeTiledFn)fn;
   if (const char* e = getenv("VMGB_NO_WST")) g_no_wst = atoi(e);
-  if (const char* e = getenv("VMGB_PDL")) g_pdl = atoi(e);      // A/B switch for tools/microbench.py
+  if (const char* e = getenv("VMGB_PDL")) g_pdl = atoi(e);
+  if (const char* e = getenv("VMGB_WS2_MULTI")) g_ws2_multi = atoi(e);
+  if (const char* e = getenv("VMGB_WST_GATE")) g_wst_gate = atoi(e);      // A/B switch for tools/microbench.py
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1264,14 +1287,18 @@ static bool encode_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuint6
   return r == CUDA_SUCCESS;
 }
 
+constexpr int WS2_MAX_BOXES_HOST = 36;
 constexpr int WST_BYTES = 8 * 4096;     // run_epilogue_w: one 32-row x 64-column bf16 buffer per epilogue warp
 
 // whether the warp-private transposition epilogue applies (see run_epilogue_w_t)
-static bool wst_ok(int NT, int Cout_g, const void* out, int out_dt, int out_pitch, int ps, int epi, const void* res, int res_dt, int res_pitch) {
+static bool wst_ok(int NT, int Cout_g, const void* out, int out_dt, int out_pitch, int ps, int epi, const void* res, int res_dt, int res_pitch,
+                   const void* aux = nullptr, int aux_dt = 0, int aux_pitch = 0) {
   if (g_no_wst) return false;
   if (out_dt != VMGB_BF16 || ps != 0 || (out_pitch & 7) || (Cout_g & 7) || (reinterpret_cast<uintptr_t>(out) & 15)) return false;
   if (epi == VMGB_EPI_STORE) return true;
-  return epi == VMGB_EPI_RESADD && res_dt == VMGB_BF16 && !(res_pitch & 7) && !(reinterpret_cast<uintptr_t>(res) & 15) && NT <= 128;      // one pass per warp
+  const bool res_ok = res_dt == VMGB_BF16 && !(res_pitch & 7) && !(reinterpret_cast<uintptr_t>(res) & 15) && NT <= 128;      // one pass per warp
+  if (epi == VMGB_EPI_RESADD) return res_ok;
+  return epi == VMGB_EPI_GATE && g_wst_gate && res_ok && aux && aux_dt == VMGB_BF16 && !(aux_pitch & 7) && !(reinterpret_cast<uintptr_t>(aux) & 15);
 }
 
 }  // namespace vmgb
@@ -1315,11 +1342,12 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0; p.res_smem = 0; p.out_smem = 0; p.aux_smem = 0;
   const int budget = g_smem_optin - 1024 - 512 - 1024;     // alignment slack, barriers, bias staging
 
-  // ---- CTA-pair weight-stationary 3x3 kernel (variant 13, or auto): single source (grouped or not)
+  // ---- CTA-pair weight-stationary 3x3 kernel (variant 13, or auto): grouped single-source convs, or ungrouped with up
+  //      to 3 equally wide sources (virtual concat)
   if (variant >= 32) { p.dbg = (variant >> 5) & 15; variant = 13; }      // probes: 13 + 32*dbg
-  if (R == 3 && S == 3 && H >= 8 && W >= 8 && n_src == 1 && (variant == 0 || variant == 13)) {
+  if (R == 3 && S == 3 && H >= 8 && W >= 8 && (n_src == 1 || (groups == 1 && (g_ws2_multi || variant == 13))) && (variant == 0 || variant == 13)) {
     const int ubytes = (18 * 10 * 128 + 1023) / 1024 * 1024;
-    const int nboxes = 9 * p.kb_per_src;                  // SWIZZLE_128B weight boxes {64 k, NT/2 rows}
+    const int nboxes = 9 * n_src * p.kb_per_src;          // SWIZZLE_128B weight boxes {64 k, NT/2 rows}
     const long long n_mt = (long long)n_img * ((H + 15) / 16) * ((W + 7) / 8);
     const long long n_pairs = (n_mt + 1) / 2;
     int best_slices = 0, best_nt = 0, best_ra = 0, best_res = 0, best_out = 0, best_wst = 0;
@@ -1344,20 +1372,25 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       if (ra >= 2) { best_slices = sl; best_nt = nts; best_ra = ra > 6 ? 6 : ra; best_res = resb; best_out = outb; best_wst = wst; }
     }
     const long long clusters_max = (g_num_sms / 2) / (groups * (best_slices ? best_slices : 1));
-    const bool worth = best_slices && clusters_max >= 1 && n_pairs >= 3 * clusters_max && p.kb_per_src <= 3;
-    if (best_slices && clusters_max >= 1 && nboxes <= 28 && (variant == 13 || worth)) {       // 28 weight-box barriers in the kernel
-      if (reinterpret_cast<uintptr_t>(x) & 15) return VMGB_EINVAL;
+    const bool worth = best_slices && clusters_max >= 1 && n_pairs >= 3 * clusters_max && n_src * p.kb_per_src <= 4;
+    if (best_slices && clusters_max >= 1 && nboxes <= WS2_MAX_BOXES_HOST && (variant == 13 || worth)) {       // weight-box barriers in the kernel
       p.nt_per_g = best_slices; p.NT = best_nt; p.b_stage_bytes = (best_nt / 2) * 128; p.ra = best_ra; p.out_smem = best_out;
       p.wst = best_wst; p.res_smem = best_wst ? 0 : best_res;
       p.BH = 16; p.BW = 8; p.a_unit_bytes = ubytes; p.stages = 0;
       p.tiles_h = (H + 15) / 16; p.tiles_w = (W + 7) / 8;
       p.total_tiles = n_mt * groups * p.nt_per_g;
-      CUtensorMap mA, mB;
+      CUtensorMap mA[3], mB;
       {
-        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
-        cuuint64_t str[3] = {(cuuint64_t)x_pitch * 2, (cuuint64_t)W * x_pitch * 2, (cuuint64_t)H * W * x_pitch * 2};
-        cuuint32_t box[4] = {64, 10, 18, 1};
-        if (!encode_bf16(&mA, x, 4, dims, str, box)) return VMGB_EINVAL;
+        const void* srcs[3] = {x, x1, x2};
+        const int c_extent = n_src > 1 ? p.Cs : Cin;
+        for (int s = 0; s < 3; ++s) {
+          const void* ptr = s < n_src ? srcs[s] : x;
+          if (reinterpret_cast<uintptr_t>(ptr) & 15) return VMGB_EINVAL;
+          cuuint64_t dims[4] = {(cuuint64_t)c_extent, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+          cuuint64_t str[3] = {(cuuint64_t)x_pitch * 2, (cuuint64_t)W * x_pitch * 2, (cuuint64_t)H * W * x_pitch * 2};
+          cuuint32_t box[4] = {64, 10, 18, 1};
+          if (!encode_bf16(&mA[s], ptr, 4, dims, str, box)) return VMGB_EINVAL;
+        }
       }
       {
         cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)groups * 9 * Cout_g};
@@ -1373,7 +1406,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
-      cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel, mA, mB, p);
+      cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel, mA[0], mA[1], mA[2], mB, p);
       if (e != cudaSuccess) { g_last_cuda_error = (int)e; return VMGB_ECUDA; }
       return check_launch();
     }
@@ -1453,8 +1486,10 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
   p.res_smem = 0; p.out_smem = 0; p.aux_smem = 0;
   int epi_smem = 0;
-  if (wst_ok(p.NT, Cout_g, out, out_dt, out_pitch, pixel_shuffle, epi, res, res_dt, res_pitch) && (budget - WST_BYTES) / stage_bytes >= 3) {
-    p.wst = 1; epi_smem = WST_BYTES;      // warp-private transposition staging: coalesced residual reads and output writes
+  const int wst_bytes = epi == VMGB_EPI_GATE ? 2 * WST_BYTES : WST_BYTES;
+  if (wst_ok(p.NT, Cout_g, out, out_dt, out_pitch, pixel_shuffle, epi, res, res_dt, res_pitch, aux, aux_dt, aux_pitch) &&
+      (budget - wst_bytes) / stage_bytes >= 3) {
+    p.wst = 1; epi_smem = wst_bytes;      // warp-private transposition staging: coalesced residual / gate reads and output writes
   } else {
     // residual staging (128 rows x NT bf16, one item ahead) when it leaves at least 4 pipeline stages
     if (epi != VMGB_EPI_STORE && res_dt == VMGB_BF16 && pixel_shuffle == 0 && (budget - p.NT * 256) / stage_bytes >= 4)
