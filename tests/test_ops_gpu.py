@@ -158,6 +158,10 @@ def test_row_kernels(dtype, tol):
     # narrow rows (C = 112: half-warp-per-row bf16 kernel), ragged row count
     xn = rnd(1037, 112, seed=20).to(dtype)
     close(ops.layernorm(xn.to(DEV), g[:112].to(DEV), b[:112].to(DEV)), emu.layernorm(xn, g[:112], b[:112]), tol)
+    close(ops.l2norm(xn.to(DEV)), emu.l2norm(xn), tol)
+    x224 = rnd(531, 224, seed=23).to(dtype)
+    g2, b2 = rnd(224, seed=24), rnd(224, seed=25)
+    close(ops.layernorm(x224.to(DEV), g2.to(DEV), b2.to(DEV)), emu.layernorm(x224, g2, b2), tol)
     # larger ragged Morph-FC case: several blocks per warp, H and W not multiples of the chunk
     x5 = rnd(2, 21, 27, 112, seed=21).to(dtype)
     for axis, chunk in ((0, 8), (1, 16), (0, 16), (1, 8)):

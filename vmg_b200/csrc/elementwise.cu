@@ -164,57 +164,80 @@ __global__ void __launch_bounds__(256) unpair_sweeps_kernel(const uint4* __restr
   }
 }
 
-// bf16 rows of up to 128 channels (C % 8 == 0): a HALF-warp owns a row, 16 bytes per lane, ROWS independent rows
-// in flight per half-warp (the 8-byte-per-lane kernel above leaves most of the HBM latency exposed: measured
-// 1.1 TB/s at C = 112)
-template <int ROWS>
-__global__ void __launch_bounds__(256) layernorm_half_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                             long long rows, int C, float eps) {
-  const int hl = threadIdx.x & 15, hsel = (threadIdx.x >> 4) & 1;
+// bf16 rows, C % 8 == 0: LPR lanes own a row (LPR = 16: C <= 128, a half-warp; LPR = 32: C <= 256), 16 bytes per lane, ROWS
+// independent rows in flight per lane group (the 8-byte-per-lane kernels above leave most of the HBM latency exposed:
+// measured 1.1 TB/s at C = 112 against 4.7 TB/s here).  MODE 0 = LayerNorm, MODE 1 = L2 normalise (F.normalize, eps 1e-12).
+template <int LPR, int ROWS, int MODE>
+__global__ void __launch_bounds__(256) rownorm16_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch, __nv_bfloat16* __restrict__ out,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        long long rows, int C, float eps) {
+  constexpr int GPW = 32 / LPR;                                   // row groups per warp
+  const int hl = threadIdx.x & (LPR - 1), hsel = (threadIdx.x & 31) / LPR;
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int c = 8 * hl;
   const bool act = c < C;
   float g[8], b[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { g[k] = act ? gamma[c + k] : 0.f; b[k] = act ? beta[c + k] : 0.f; }
+  for (int k = 0; k < 8; ++k) { g[k] = (MODE == 0 && act) ? gamma[c + k] : 0.f; b[k] = (MODE == 0 && act) ? beta[c + k] : 0.f; }
   const float inv_c = 1.f / (float)C;
-  // the loop bound is uniform over the warp (both half-warps take part in every full-mask shuffle)
-  for (long long w0 = warp_id * 2 * ROWS; w0 < rows; w0 += n_warps * 2 * ROWS) {
+  // the loop bound is uniform over the warp (every lane takes part in every full-mask shuffle)
+  for (long long w0 = warp_id * GPW * ROWS; w0 < rows; w0 += n_warps * GPW * ROWS) {
     const long long r0 = w0 + hsel * ROWS;
     uint4 raw[ROWS];
 #pragma unroll
     for (int k = 0; k < ROWS; ++k)
-      raw[k] = (act && r0 + k < rows) ? __ldg(reinterpret_cast<const uint4*>(x + (r0 + k) * C + c)) : make_uint4(0, 0, 0, 0);
+      raw[k] = (act && r0 + k < rows) ? __ldg(reinterpret_cast<const uint4*>(x + (r0 + k) * x_pitch + c)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int k = 0; k < ROWS; ++k) {
       float v[8];
       const uint32_t w[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) { v[2 * q] = __uint_as_float(w[q] << 16); v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u); }
-      float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+      uint32_t o[4];
+      if (MODE == 0) {
+        float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
 #pragma unroll
-      for (int m = 8; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-      const float mean = s * inv_c;
-      float q2 = 0.f;
+        for (int m = LPR / 2; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+        const float mean = s * inv_c;
+        float q2 = 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { v[e] -= mean; q2 += v[e] * v[e]; }
-      q2 = act ? q2 : 0.f;
+        for (int e = 0; e < 8; ++e) { v[e] -= mean; q2 += v[e] * v[e]; }
+        q2 = act ? q2 : 0.f;
 #pragma unroll
-      for (int m = 8; m >= 1; m >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, m);
-      const float rstd = rsqrtf(q2 * inv_c + eps);
-      if (act && r0 + k < rows) {
-        uint32_t o[4];
+        for (int m = LPR / 2; m >= 1; m >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, m);
+        const float rstd = rsqrtf(q2 * inv_c + eps);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q] * rstd * g[2 * q] + b[2 * q], v[2 * q + 1] * rstd * g[2 * q + 1] + b[2 * q + 1]);
           o[q] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        *reinterpret_cast<uint4*>(out + (r0 + k) * C + c) = make_uint4(o[0], o[1], o[2], o[3]);
+      } else {
+        float q2 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) q2 += v[e] * v[e];
+#pragma unroll
+        for (int m = LPR / 2; m >= 1; m >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, m);
+        const float inv = 1.f / fmaxf(sqrtf(q2), 1e-12f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q] * inv, v[2 * q + 1] * inv);
+          o[q] = *reinterpret_cast<const uint32_t*>(&h);
+        }
       }
+      if (act && r0 + k < rows) *reinterpret_cast<uint4*>(out + (r0 + k) * C + c) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
+}
+
+template <int MODE>
+static void launch_rownorm16(const void* x, int x_pitch, void* out, const float* gamma, const float* beta, long long rows, int C, float eps,
+                             cudaStream_t st) {
+  const int lpr = C <= 128 ? 16 : 32, rows_per_warp_iter = (32 / lpr) * (lpr == 16 ? 8 : 4);
+  const long long wanted = (rows + 8LL * rows_per_warp_iter - 1) / (8LL * rows_per_warp_iter);
+  const unsigned nb = (unsigned)(wanted < 148 * 6 ? (wanted < 1 ? 1 : wanted) : 148 * 6);
+  if (lpr == 16) rownorm16_kernel<16, 8, MODE><<<nb, 256, 0, st>>>((const __nv_bfloat16*)x, x_pitch, (__nv_bfloat16*)out, gamma, beta, rows, C, eps);
+  else rownorm16_kernel<32, 4, MODE><<<nb, 256, 0, st>>>((const __nv_bfloat16*)x, x_pitch, (__nv_bfloat16*)out, gamma, beta, rows, C, eps);
 }
 
 // L2 normalise (F.normalize, eps 1e-12)
@@ -693,11 +716,8 @@ extern "C" int vmgb_layernorm(const void* x, int x_dt, void* out, int out_dt, co
   if (!x || !out || !gamma || !beta || !dt_ok(x_dt) || !dt_ok(out_dt) || C <= 0 || C > 32 * MAXV || rows <= 0) return VMGB_EINVAL;
   long long blocks = (rows + 7) / 8;
   const bool vec = (C & 3) == 0 && !((uintptr_t)x & 15) && !((uintptr_t)out & 15) && !((uintptr_t)gamma & 15) && !((uintptr_t)beta & 15);
-  if (vec && C <= 128 && (C & 7) == 0 && x_dt == VMGB_BF16 && out_dt == VMGB_BF16) {
-    const long long wanted = (rows + 16 * 8 - 1) / (16 * 8);          // 16 half-warps per block, 8 rows each per iteration
-    const unsigned nb = (unsigned)(wanted < 148 * 6 ? (wanted < 1 ? 1 : wanted) : 148 * 6);
-    layernorm_half_kernel<8><<<nb, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, (const float*)gamma,
-                                                                 (const float*)beta, rows, C, eps);
+  if (vec && C <= 256 && (C & 7) == 0 && x_dt == VMGB_BF16 && out_dt == VMGB_BF16) {
+    launch_rownorm16<0>(x, C, out, (const float*)gamma, (const float*)beta, rows, C, eps, as_stream(stream));
   } else if (vec && C <= 128) {
     const long long wanted = (rows + 8 * 4 - 1) / (8 * 4);
     const unsigned nb = (unsigned)(wanted < 148 * 8 ? (wanted < 1 ? 1 : wanted) : 148 * 8);
@@ -712,7 +732,9 @@ extern "C" int vmgb_l2norm(const void* x, int x_dt, int x_pitch, void* out, int 
   if (!x || !out || !dt_ok(x_dt) || !dt_ok(out_dt) || C <= 0 || C > 32 * MAXV || rows <= 0) return VMGB_EINVAL;
   long long blocks = (rows + 7) / 8;
   const bool vec = (C & 3) == 0 && (x_pitch & 3) == 0 && !((uintptr_t)x & 15) && !((uintptr_t)out & 15);
-  if (vec) l2norm_vec_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, x_dt, x_pitch, out, out_dt, rows, C);
+  if (vec && C <= 256 && (C & 7) == 0 && (x_pitch & 7) == 0 && x_dt == VMGB_BF16 && out_dt == VMGB_BF16)
+    launch_rownorm16<1>(x, x_pitch, out, nullptr, nullptr, rows, C, 0.f, as_stream(stream));
+  else if (vec) l2norm_vec_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, x_dt, x_pitch, out, out_dt, rows, C);
   else
   l2norm_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, x_dt, x_pitch, out, out_dt, rows, C);
   return check_launch();
