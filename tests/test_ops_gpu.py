@@ -120,10 +120,12 @@ def test_conv3x3_variants(case, variant, out_dtype, tol):
 @pytest.mark.parametrize('case', [(2, 24, 24, 8, 32, 7, 1, ops.ACT_RELU, ops.EPI_STORE, 0, 1), (2, 12, 20, 64, 32, 7, 1, ops.ACT_RELU, ops.EPI_STORE, 0, 1),
                                   (1, 20, 20, 16, 2, 7, 1, ops.ACT_NONE, ops.EPI_RESADD, 0, 1), (3, 33, 41, 32, 64, 7, 1, ops.ACT_RELU, ops.EPI_STORE, 0, 1)],
                          ids=lambda c: 'x'.join(map(str, c)))
-def test_conv7x7_weight_stationary(case):
+@pytest.mark.parametrize('variant', [8, 13, 0], ids=['weight_stationary', 'weight_stationary_cta_pair', 'auto'])
+@pytest.mark.parametrize('out_dtype,tol', [(torch.float32, 2e-3), (torch.bfloat16, 2e-2)], ids=['out_f32', 'out_bf16'])
+def test_conv7x7_weight_stationary(case, variant, out_dtype, tol):
     N, H, W, Cin, Cout, R, groups, act, epi, ps, n_src = case
-    out, ref = conv_case(N, H, W, Cin, Cout, R, groups, torch.bfloat16, True, n_src, act, epi, ps, out_dtype=torch.float32, variant=8)
-    close(out, ref, 2e-3)
+    out, ref = conv_case(N, H, W, Cin, Cout, R, groups, torch.bfloat16, True, n_src, act, epi, ps, out_dtype=out_dtype, variant=variant)
+    close(out, ref, tol)
 
 
 def test_conv_tcgen05_many_tiles_persistent():

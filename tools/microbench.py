@@ -78,7 +78,7 @@ def run_conv(iters, only=None, variants=(0,)):
             ops.conv2d(xs if n_src > 1 else xs[0], pc, act=act, alpha=0.1, epi=epi, res=res, aux=aux, res_scale=0.1, pixel_shuffle=ps, out=o, tc_variant=1)
             ref = o.float().clone()
         for variant in variants:
-            if (1 < variant < 8 and R != 3) or (variant == 8 and R not in (3, 7)) or (variant > 8 and R != 3):
+            if (1 < variant < 8 and R != 3) or (variant == 8 and R not in (3, 7)) or (variant > 8 and variant != 13 and variant < 32 and R != 3):
                 continue
             fn = lambda: ops.conv2d(xs if n_src > 1 else xs[0], pc, act=act, alpha=0.1, epi=epi, res=res, aux=aux, res_scale=0.1, pixel_shuffle=ps, out=o, tc_variant=variant)
             try:

@@ -1073,13 +1073,16 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 // Work split: cluster c owns combo = c % slices and walks the tile PAIRS c / slices, + clusters / slices, ...
 // (tile 2t -> rank 0, tile 2t+1 -> rank 1; an odd tail tile is loaded fully out of bounds = zeros).
 // ---------------------------------------------------------------------------------------------
-constexpr int WS2_MAX_BOXES = 36;      // weight-box barriers: 9 taps x up to 4 K blocks
+// R = 7 (SPyNet): the same kernel with {64 ch, 14 cols, 22 rows} units; one weight barrier per kernel ROW (7 boxes).
+constexpr int WS2_MAX_BOXES = 36;      // weight barriers: 9 taps x up to 4 K blocks (R = 3), 7 kernel rows x up to 4 K blocks (R = 7)
+template <int RR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB, const TcP p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  constexpr int RR = 3, BWX = 10, TAPS = 9, UROWS = 18;
+  constexpr int BWX = 8 + RR - 1, TAPS = RR * RR, UROWS = 16 + RR - 1, PADR = RR / 2;
+  constexpr int WG = RR == 3 ? 1 : RR;              // weight boxes per barrier
   // weights: one SWIZZLE_128B box {64 k, N/2 rows} per (K block, tap).  (A dense SWIZZLE_32B layout, one {16 k, N/2}
   // box per K = 16 slice, saves 16 KB at C = 112 but measured ~25 % slower MMA issue on B200.)
   const int nkb = p.n_src * p.kb_per_src;              // K blocks of one tile: (source of the virtual concat, 64-channel block)
@@ -1098,7 +1101,7 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.ra; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
-    for (int i = 0; i < nboxes; ++i) mbar_init(wfull0 + 8 * i, 1);
+    for (int i = 0; i < nboxes / WG; ++i) mbar_init(wfull0 + 8 * i, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 512); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
@@ -1133,8 +1136,8 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         for (int tap = 0; tap < TAPS; ++tap) {
           const int box = kbt * TAPS + tap;
           const int src = kbt / p.kb_per_src, kb = kbt - src * p.kb_per_src;
-          if (rank == 0) mbar_expect_tx(wfull0 + 8 * box, (uint32_t)(2 * NH * 128));
-          tma_load_2d_2sm(w_base + box * p.b_stage_bytes, &mapB, wfull0_l + 8 * box, src * p.Cs + kb * 64,
+          if (rank == 0 && box % WG == 0) mbar_expect_tx(wfull0 + 8 * (box / WG), (uint32_t)(2 * WG * NH * 128));
+          tma_load_2d_2sm(w_base + box * p.b_stage_bytes, &mapB, wfull0_l + 8 * (box / WG), src * p.Cs + kb * 64,
                           (g * TAPS + tap) * p.Cout_g + nt * p.NT + (int)rank * NH);
         }
     }
@@ -1158,7 +1161,7 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           if (p.dbg & 4) { if (rank == 0) mbar_arrive(afull0 + 8 * ia); }
           else {
             if (rank == 0) mbar_expect_tx(afull0 + 8 * ia, 2 * a_bytes);
-            tma_load_4d_2sm(a_base + ia * p.a_unit_bytes, mA, afull0_l + 8 * ia, ca, w0 - 1, h0 - 1, img);
+            tma_load_4d_2sm(a_base + ia * p.a_unit_bytes, mA, afull0_l + 8 * ia, ca, w0 - PADR, h0 - PADR, img);
           }
         }
         __syncwarp();
@@ -1189,7 +1192,7 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         if (!(p.dbg & 1)) {
 #pragma unroll
           for (int tap = 0; tap < TAPS; ++tap) {
-            if (it == 0) { mbar_wait(wfull0 + 8 * (kbt * TAPS + tap), 0); tc_fence_after(); }     // weights of this box have landed (first tile only)
+            if (it == 0 && tap % WG == 0) { mbar_wait(wfull0 + 8 * ((kbt * TAPS + tap) / WG), 0); tc_fence_after(); }     // weights have landed (first tile only)
             const uint64_t ad = smem_desc_sw128_sbo(a_unit + (uint32_t)((tap / RR) * BWX + (tap % RR)) * 128u, (uint32_t)BWX * 128u);
             const uint64_t bd = smem_desc_sw128(w_base + (kbt * TAPS + tap) * p.b_stage_bytes);
             for (int ks = 0; ks < nks; ++ks)
@@ -1274,7 +1277,8 @@ static void tc_init() {
     cudaFuncSetAttribute(conv3x3_ws_kernel<7, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
     cudaFuncSetAttribute(conv3x3_ws_kernel<3, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
     cudaFuncSetAttribute(conv3x3_ws_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-    cudaFuncSetAttribute(conv3x3_ws2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+    cudaFuncSetAttribute(conv3x3_ws2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+    cudaFuncSetAttribute(conv3x3_ws2_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
   }
 }
 
@@ -1345,9 +1349,11 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   // ---- CTA-pair weight-stationary 3x3 kernel (variant 13, or auto): grouped single-source convs, or ungrouped with up
   //      to 3 equally wide sources (virtual concat)
   if (variant >= 32) { p.dbg = (variant >> 5) & 15; variant = 13; }      // probes: 13 + 32*dbg
-  if (R == 3 && S == 3 && H >= 8 && W >= 8 && (n_src == 1 || (groups == 1 && (g_ws2_multi || variant == 13))) && (variant == 0 || variant == 13)) {
-    const int ubytes = (18 * 10 * 128 + 1023) / 1024 * 1024;
-    const int nboxes = 9 * n_src * p.kb_per_src;          // SWIZZLE_128B weight boxes {64 k, NT/2 rows}
+  if (R == S && (R == 3 || R == 7) && H >= 8 && W >= 8 && (n_src == 1 || (groups == 1 && (g_ws2_multi || variant == 13))) &&
+      (variant == 0 || variant == 13)) {
+    const int ubytes = ((16 + R - 1) * (8 + R - 1) * 128 + 1023) / 1024 * 1024;
+    const int nboxes = R * R * n_src * p.kb_per_src;      // SWIZZLE_128B weight boxes {64 k, NT/2 rows}
+    const int nbars = nboxes / (R == 3 ? 1 : R);
     const long long n_mt = (long long)n_img * ((H + 15) / 16) * ((W + 7) / 8);
     const long long n_pairs = (n_mt + 1) / 2;
     int best_slices = 0, best_nt = 0, best_ra = 0, best_res = 0, best_out = 0, best_wst = 0;
@@ -1373,7 +1379,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
     }
     const long long clusters_max = (g_num_sms / 2) / (groups * (best_slices ? best_slices : 1));
     const bool worth = best_slices && clusters_max >= 1 && n_pairs >= 3 * clusters_max && n_src * p.kb_per_src <= 4;
-    if (best_slices && clusters_max >= 1 && nboxes <= WS2_MAX_BOXES_HOST && (variant == 13 || worth)) {       // weight-box barriers in the kernel
+    if (best_slices && clusters_max >= 1 && nbars <= WS2_MAX_BOXES_HOST && (variant == 13 || worth)) {       // weight-box barriers in the kernel
       p.nt_per_g = best_slices; p.NT = best_nt; p.b_stage_bytes = (best_nt / 2) * 128; p.ra = best_ra; p.out_smem = best_out;
       p.wst = best_wst; p.res_smem = best_wst ? 0 : best_res;
       p.BH = 16; p.BW = 8; p.a_unit_bytes = ubytes; p.stages = 0;
@@ -1388,12 +1394,12 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
           if (reinterpret_cast<uintptr_t>(ptr) & 15) return VMGB_EINVAL;
           cuuint64_t dims[4] = {(cuuint64_t)c_extent, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
           cuuint64_t str[3] = {(cuuint64_t)x_pitch * 2, (cuuint64_t)W * x_pitch * 2, (cuuint64_t)H * W * x_pitch * 2};
-          cuuint32_t box[4] = {64, 10, 18, 1};
+          cuuint32_t box[4] = {64, (cuuint32_t)(8 + R - 1), (cuuint32_t)(16 + R - 1), 1};
           if (!encode_bf16(&mA[s], ptr, 4, dims, str, box)) return VMGB_EINVAL;
         }
       }
       {
-        cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)groups * 9 * Cout_g};
+        cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)groups * R * R * Cout_g};
         cuuint64_t str[1] = {(cuuint64_t)Kp * 2};
         cuuint32_t box[2] = {64, (cuuint32_t)(p.NT / 2)};
         if (!encode_bf16(&mB, w, 2, dims, str, box)) return VMGB_EINVAL;
@@ -1406,7 +1412,8 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
-      cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel, mA[0], mA[1], mA[2], mB, p);
+      cudaError_t e = R == 3 ? cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel<3>, mA[0], mA[1], mA[2], mB, p)
+                             : cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel<7>, mA[0], mA[1], mA[2], mB, p);
       if (e != cudaSuccess) { g_last_cuda_error = (int)e; return VMGB_ECUDA; }
       return check_launch();
     }
