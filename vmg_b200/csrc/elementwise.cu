@@ -388,9 +388,16 @@ __global__ void __launch_bounds__(32 * MORPH_WARPS) morph_block16_kernel(const _
   const unsigned short* sme = reinterpret_cast<const unsigned short*>(smv);
   const float inv_S = 1.f / (float)S, inv_Cv = 1.f / (float)Cv, inv_Cpv = 1.f / (float)Cpv;
   const long long wstride = (long long)gridDim.x * MORPH_WARPS;
-  for (long long blk = (long long)blockIdx.x * MORPH_WARPS + wid; blk < n_blocks; blk += wstride) {
-    // block index = (bt*O + o)*Lg + lg  (same order as the row index / ch)
-    const int lg = (int)(blk % Lg); const long long t = blk / Lg; const int o = (int)(t % O); const int bt = (int)(t / O);
+  for (long long wi = (long long)blockIdx.x * MORPH_WARPS + wid; wi < n_blocks; wi += wstride) {
+    // block index = (bt*O + o)*Lg + lg  (same order as the row index / ch).  Work order: for axis 0 the pixel rows of a
+    // block are W*C apart, so neighbouring warps take neighbouring o (= w) and the pixel side of the traffic is one
+    // contiguous run per image row (measured neutral on B200: the kernel is paced by the 2-byte shared-memory reads of
+    // the transposition - 4-way bank conflicts at S = 14 - not by DRAM locality).
+    int lg, o, bt;
+    const unsigned wu = (unsigned)wi;                  // the host caps n_blocks below 2^31: 32-bit divisions
+    if (axis == 0) { o = (int)(wu % (unsigned)O); const unsigned t = wu / (unsigned)O; lg = (int)(t % (unsigned)Lg); bt = (int)(t / (unsigned)Lg); }
+    else { lg = (int)(wu % (unsigned)Lg); const unsigned t = wu / (unsigned)Lg; o = (int)(t % (unsigned)O); bt = (int)(t / (unsigned)O); }
+    const long long blk = ((long long)bt * O + o) * Lg + lg;
     const long long rows0 = blk * ch;
     if (!inverse) {
       // 1. ch pixel rows -> sm[r*C + c]
@@ -748,7 +755,7 @@ extern "C" int vmgb_morph_permute(const void* src, int src_dt, void* dst, int ds
   const int L = axis == 0 ? H : W, Lp = (L + chunk - 1) / chunk * chunk, O = axis == 0 ? W : H;
   const long long n_blocks_all = (long long)BT * O * (Lp / chunk);
   if (src_dt == VMGB_BF16 && dst_dt == VMGB_BF16 && (C & 7) == 0 && (Cp & 7) == 0 && (a_pitch & 7) == 0 &&
-      !(((uintptr_t)src | (uintptr_t)dst) & 15) && (size_t)chunk * Cp * 2 * MORPH_WARPS <= 48 * 1024 && Cp < 4096) {
+      !(((uintptr_t)src | (uintptr_t)dst) & 15) && (size_t)chunk * Cp * 2 * MORPH_WARPS <= 48 * 1024 && Cp < 4096 && n_blocks_all < 2147483647LL) {
     const size_t smem = (size_t)chunk * Cp * 2 * MORPH_WARPS;        // C <= Cp
     const long long wanted = (n_blocks_all + MORPH_WARPS - 1) / MORPH_WARPS;
     const unsigned grid = (unsigned)(wanted < 148 * 16 ? wanted : 148 * 16);
