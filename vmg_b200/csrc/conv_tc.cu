@@ -1132,10 +1132,10 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
     // ===================== TMA producer (both CTAs) =====================
     const uint32_t wfull0_l = mapa_rank(wfull0, 0), afull0_l = mapa_rank(afull0, 0);
     if (elect_one()) {                 // this CTA's half of the weight slice, once, in the order the MMAs consume it
-      for (int kbt = 0; kbt < nkb; ++kbt)
+      for (int src = 0, kbt = 0; src < p.n_src; ++src)
+       for (int kb = 0; kb < p.kb_per_src; ++kb, ++kbt)
         for (int tap = 0; tap < TAPS; ++tap) {
           const int box = kbt * TAPS + tap;
-          const int src = kbt / p.kb_per_src, kb = kbt - src * p.kb_per_src;
           if (rank == 0 && box % WG == 0) mbar_expect_tx(wfull0 + 8 * (box / WG), (uint32_t)(2 * WG * NH * 128));
           tma_load_2d_2sm(w_base + box * p.b_stage_bytes, &mapB, wfull0_l + 8 * (box / WG), src * p.Cs + kb * 64,
                           (g * TAPS + tap) * p.Cout_g + nt * p.NT + (int)rank * NH);
@@ -1152,8 +1152,8 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         img = (int)(mt / tiles_per_img); const int rem = (int)(mt % tiles_per_img);
         h0 = (rem / p.tiles_w) * 16; w0 = (rem % p.tiles_w) * 8;
       }
-      for (int kbt = 0; kbt < nkb; ++kbt) {
-        const int src = kbt / p.kb_per_src, kb = kbt - src * p.kb_per_src;
+      for (int src = 0; src < p.n_src; ++src)
+      for (int kb = 0; kb < p.kb_per_src; ++kb) {
         const CUtensorMap* mA = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
         const int ca = (p.n_src > 1 ? 0 : ((g * p.Cin_g) & ~7)) + kb * 64;
         mbar_wait(aempty0 + 8 * ia, pa ^ 1);
@@ -1183,8 +1183,7 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
       uint32_t accumulate = 0;
-      for (int kbt = 0; kbt < nkb; ++kbt) {
-        const int kb = kbt % p.kb_per_src;
+      for (int kbt = 0, kb = 0; kbt < nkb; ++kbt, kb = (kb + 1 == p.kb_per_src ? 0 : kb + 1)) {
         const int nks = min(4, (p.Cs + koff - kb * 64 + 15) >> 4);
         mbar_wait(afull0 + 8 * ia, pa);
         tc_fence_after();
