@@ -56,6 +56,14 @@ GENERIC = [
 ]
 
 
+@pytest.mark.parametrize('out_dtype,tol', [(torch.float32, 2e-5), (torch.bfloat16, 1e-2)], ids=['out_f32', 'out_bf16'])
+def test_input_proj_small_cin_kernel(out_dtype, tol):
+    # first conv of the network (3 -> C, fp32 frames in): the direct small-Cin kernel takes launches of >= 4096 pixels
+    for Cout, act in ((112, ops.ACT_LRELU), (144, ops.ACT_LRELU), (64, ops.ACT_NONE)):
+        out, ref = conv_case(2, 49, 67, 3, Cout, 3, 1, torch.float32, False, 1, act, ops.EPI_STORE, 0, out_dtype=out_dtype)
+        close(out, ref, tol)
+
+
 @pytest.mark.parametrize('case', GENERIC, ids=lambda c: 'x'.join(map(str, c)))
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['f32', 'bf16'])
 def test_conv_generic(case, dtype):

@@ -227,6 +227,64 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 3x3 convolution with a tiny input (Cin <= 4, fp32 NHWC, one group, plain store): the network's first conv
+// (input_proj 3 -> C, vmg.py:378-386).  K = 27 is far too small for the implicit-GEMM tiles above (6.5 ms for the
+// headline clip, 5 TFLOP/s); here a thread owns 8 output channels of one pixel, the packed weights [tap][ci][co] and
+// the bias live in shared memory (broadcast across the pixels of a warp), the 27 inputs come through L1, and the
+// 14 threads of a pixel write its 224-byte channel run as consecutive 16-byte pieces.  FMA-pipe bound.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv3x3_smallcin_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, void* out, int out_dt, int out_pitch,
+                                                               int n_img, int H, int W, int Cin, int Cout, int act, float alpha,
+                                                               float out_scale, long long n_pix) {
+  extern __shared__ float smw[];                 // [9*Cin][Cout] weights, then [Cout] bias
+  const int nw = 9 * Cin * Cout;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) smw[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) smw[nw + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int ngrp = Cout >> 3;                    // 8-channel groups per pixel
+  const int ppb = blockDim.x / ngrp;             // pixels per block iteration
+  const int slot = threadIdx.x / ngrp, cg = threadIdx.x - slot * ngrp;
+  if (slot >= ppb) return;
+  const int co = cg * 8;
+  for (long long pix = (long long)blockIdx.x * ppb + slot; pix < n_pix; pix += (long long)gridDim.x * ppb) {
+    const int ww = (int)(pix % W); const long long t = pix / W; const int hh = (int)(t % H); const int img = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = smw[nw + co + j];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int y = hh + tap / 3 - 1, xx = ww + tap % 3 - 1;
+      if (y < 0 || y >= H || xx < 0 || xx >= W) continue;
+      const float* xp = x + (((long long)img * H + y) * W + xx) * x_pitch;
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float xv = __ldg(xp + ci);
+        const float4 w0 = *reinterpret_cast<const float4*>(smw + (tap * Cin + ci) * Cout + co);
+        const float4 w1 = *reinterpret_cast<const float4*>(smw + (tap * Cin + ci) * Cout + co + 4);
+        acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]); acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+        acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]); acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = apply_act(acc[j], act, alpha) * out_scale;
+    const long long o = pix * out_pitch + co;
+    if (out_dt == VMGB_BF16) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+        pk[q] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    } else {
+      float* op = reinterpret_cast<float*>(out) + o;
+      *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
+
 }  // namespace vmgb
 
 using namespace vmgb;
@@ -246,6 +304,19 @@ extern "C" int vmgb_conv2d_nhwc(const void* x, const void* x1, const void* x2, i
   if (pixel_shuffle != 0 && (pixel_shuffle != 2 || (Cout & 3))) return VMGB_EINVAL;
   if (n_src < 1 || n_src > 3 || (n_src > 1 && (!x1 || groups != 1 || Cin % n_src || (Cin / n_src) % BK))) return VMGB_EINVAL;
   if (n_src > 2 && !x2) return VMGB_EINVAL;
+  // first conv of the network: tiny K (the bit pattern of the summation differs from the tiled kernel: fp32, tap-major)
+  if (n_src == 1 && groups == 1 && Cin <= 4 && R == 3 && S == 3 && epi == VMGB_EPI_STORE && pixel_shuffle == 0 && x_dt == VMGB_F32 &&
+      (Cout & 7) == 0 && Cout <= 256 && (out_pitch & 7) == 0 && !(reinterpret_cast<uintptr_t>(out) & 15) &&
+      (long long)n_img * H * W >= 4096) {
+    const long long n_pix = (long long)n_img * H * W;
+    const int ppb = 256 / (Cout >> 3);
+    const long long wanted = (n_pix + ppb - 1) / ppb;
+    const unsigned grid = (unsigned)(wanted < 148 * 8 ? wanted : 148 * 8);
+    const size_t smem = (size_t)(9 * Cin * Cout + Cout) * sizeof(float);
+    conv3x3_smallcin_kernel<<<grid, 256, smem, as_stream(stream)>>>((const float*)x, x_pitch, (const float*)w, (const float*)bias, out, out_dt,
+                                                                    out_pitch, n_img, H, W, Cin, Cout, act, act_alpha, out_scale, n_pix);
+    return check_launch();
+  }
   ConvP p;
   p.x1 = x1; p.x2 = x2; p.n_src = n_src; p.Csrc = Cin / n_src;
   p.x = x; p.w = (const float*)w; p.bias = (const float*)bias; p.out = out; p.res = res; p.aux = aux;
