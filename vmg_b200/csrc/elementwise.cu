@@ -391,8 +391,8 @@ __global__ void __launch_bounds__(32 * MORPH_WARPS) morph_block16_kernel(const _
   for (long long wi = (long long)blockIdx.x * MORPH_WARPS + wid; wi < n_blocks; wi += wstride) {
     // block index = (bt*O + o)*Lg + lg  (same order as the row index / ch).  Work order: for axis 0 the pixel rows of a
     // block are W*C apart, so neighbouring warps take neighbouring o (= w) and the pixel side of the traffic is one
-    // contiguous run per image row (measured neutral on B200: the kernel is paced by the 2-byte shared-memory reads of
-    // the transposition - 4-way bank conflicts at S = 14 - not by DRAM locality).
+    // contiguous run per image row (measured neutral on B200: the kernel is paced by the instructions of the 2-byte
+    // element shuffle, not by DRAM locality; rotating the reads to dodge their 4-way bank conflicts made it slower).
     int lg, o, bt;
     const unsigned wu = (unsigned)wi;                  // the host caps n_blocks below 2^31: 32-bit divisions
     if (axis == 0) { o = (int)(wu % (unsigned)O); const unsigned t = wu / (unsigned)O; lg = (int)(t % (unsigned)Lg); bt = (int)(t / (unsigned)Lg); }
