@@ -386,6 +386,8 @@ __global__ void __launch_bounds__(32 * MORPH_WARPS) morph_block16_kernel(const _
   const int per_warp_vec = ch * (Cv > Cpv ? Cv : Cpv);
   uint4* smv = sm_vec_all + wid * per_warp_vec;
   const unsigned short* sme = reinterpret_cast<const unsigned short*>(smv);
+  const uint32_t* smw32 = reinterpret_cast<const uint32_t*>(smv);
+  const bool s_even = (S & 1) == 0 && (C & 1) == 0;
   const float inv_S = 1.f / (float)S, inv_Cv = 1.f / (float)Cv, inv_Cpv = 1.f / (float)Cpv;
   const long long wstride = (long long)gridDim.x * MORPH_WARPS;
   for (long long wi = (long long)blockIdx.x * MORPH_WARPS + wid; wi < n_blocks; wi += wstride) {
@@ -416,15 +418,28 @@ __global__ void __launch_bounds__(32 * MORPH_WARPS) morph_block16_kernel(const _
       for (int i = lane; i < ch * Cpv; i += 32) {
         const int g = (int)(((float)i + 0.5f) * inv_Cpv), f = 8 * (i - g * Cpv);
         int r = (int)(((float)f + 0.5f) * inv_S), s2 = f - r * S;
-        unsigned short e[8];
+        uint4 v;
+        if (s_even) {            // S even: element pairs never straddle a segment -> move 32-bit words
+          uint32_t wv[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int c = g * S + s2;
-          e[k] = c < C ? sme[r * C + c] : (unsigned short)0;
-          if (++s2 == S) { s2 = 0; ++r; }
+          for (int k = 0; k < 4; ++k) {
+            const int c = g * S + s2;
+            wv[k] = c < C ? smw32[(r * C + c) >> 1] : 0u;
+            s2 += 2;
+            if (s2 == S) { s2 = 0; ++r; }
+          }
+          v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        } else {
+          unsigned short e[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c = g * S + s2;
+            e[k] = c < C ? sme[r * C + c] : (unsigned short)0;
+            if (++s2 == S) { s2 = 0; ++r; }
+          }
+          v = make_uint4((uint32_t)e[0] | ((uint32_t)e[1] << 16), (uint32_t)e[2] | ((uint32_t)e[3] << 16),
+                         (uint32_t)e[4] | ((uint32_t)e[5] << 16), (uint32_t)e[6] | ((uint32_t)e[7] << 16));
         }
-        const uint4 v = make_uint4((uint32_t)e[0] | ((uint32_t)e[1] << 16), (uint32_t)e[2] | ((uint32_t)e[3] << 16),
-                                   (uint32_t)e[4] | ((uint32_t)e[5] << 16), (uint32_t)e[6] | ((uint32_t)e[7] << 16));
         *reinterpret_cast<uint4*>(dst + (rows0 + g) * a_pitch + f) = v;
       }
       __syncwarp();
@@ -441,14 +456,26 @@ __global__ void __launch_bounds__(32 * MORPH_WARPS) morph_block16_kernel(const _
         const int l = lg * ch + r;
         if (l < L) {
           int g = (int)(((float)c0 + 0.5f) * inv_S), s2 = c0 - g * S;
-          unsigned short e[8];
+          uint4 v;
+          if (s_even) {
+            uint32_t wv[4];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            e[k] = sme[g * Cp + r * S + s2];
-            if (++s2 == S) { s2 = 0; ++g; }
+            for (int k = 0; k < 4; ++k) {
+              wv[k] = smw32[(g * Cp + r * S + s2) >> 1];
+              s2 += 2;
+              if (s2 == S) { s2 = 0; ++g; }
+            }
+            v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+          } else {
+            unsigned short e[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              e[k] = sme[g * Cp + r * S + s2];
+              if (++s2 == S) { s2 = 0; ++g; }
+            }
+            v = make_uint4((uint32_t)e[0] | ((uint32_t)e[1] << 16), (uint32_t)e[2] | ((uint32_t)e[3] << 16),
+                           (uint32_t)e[4] | ((uint32_t)e[5] << 16), (uint32_t)e[6] | ((uint32_t)e[7] << 16));
           }
-          const uint4 v = make_uint4((uint32_t)e[0] | ((uint32_t)e[1] << 16), (uint32_t)e[2] | ((uint32_t)e[3] << 16),
-                                     (uint32_t)e[4] | ((uint32_t)e[5] << 16), (uint32_t)e[6] | ((uint32_t)e[7] << 16));
           const int h = axis == 0 ? l : o, w = axis == 0 ? o : l;
           *reinterpret_cast<uint4*>(dst + (((long long)bt * H + h) * W + w) * C + c0) = v;
         }
