@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <mutex>
 #include <cstdlib>
+#include <type_traits>
 
 namespace vmgb {
 
@@ -136,6 +137,19 @@ __device__ __forceinline__ void umma_f16_2sm_if(uint32_t issue, uint32_t tmem_d,
       "setp.ne.b32 q, %5, 0;\n\t"
       "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
+}
+// same with the descriptors as (low, high) 32-bit halves: the high words (stride, version, swizzle mode) are loop
+// constants and the low words (start address) advance by immediates, ~5 instructions per MMA instead of ~19
+__device__ __forceinline__ void umma_f16_2sm_if_lh(uint32_t issue, uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                   uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
 }
 __device__ __forceinline__ void umma_commit_2sm_if(uint32_t issue, uint32_t bar, uint16_t mask) {
   asm volatile(
@@ -490,22 +504,21 @@ __device__ __forceinline__ void run_epilogue_t(const TcP& p, float* bias_s, uint
       epilogue_chunk<ACT, EPI, PS>(p, raw, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, r0, r1, sd, sd + 16, hp && stage_aux, a0, a1);
     };
     {
-      uint32_t rawA[16], rawB[16];
+      // one copy of the chunk body (the two-buffer ping-pong doubled a ~700-instruction body past the L0 instruction
+      // cache: 16 % of the epilogue's stall samples were no_inst): the landed chunk moves to `work`, the next load
+      // re-uses `raw` while `work` is processed
+      uint32_t raw[16], work[16];
       int ch = half;
       __syncwarp();
-      if (ch < nchunks) tmem_ld16_issue(taddr + ch * 16, rawA);
+      if (ch < nchunks) tmem_ld16_issue(taddr + ch * 16, raw);
 #pragma unroll 1
       while (ch < nchunks) {
-        tmem_ld_wait();                                            // rawA ready
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) work[j] = raw[j];
         __syncwarp();
-        if (ch + 2 < nchunks) tmem_ld16_issue(taddr + (ch + 2) * 16, rawB);
-        process(ch, rawA);
-        ch += 2;
-        if (ch >= nchunks) break;
-        tmem_ld_wait();                                            // rawB ready
-        __syncwarp();
-        if (ch + 2 < nchunks) tmem_ld16_issue(taddr + (ch + 2) * 16, rawA);
-        process(ch, rawB);
+        if (ch + 2 < nchunks) tmem_ld16_issue(taddr + (ch + 2) * 16, raw);
+        process(ch, work);
         ch += 2;
       }
     }
@@ -671,20 +684,17 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
         }
         epilogue_chunk<ACT, EPI, 0>(p, raw, pvalid, img, hh, ww, pix, g, nt, ch0 + c, bias_s, hp, r0, r1, c0, c1, hp && has_aux, a0, a1);
       };
-      uint32_t rawA[16], rawB[16];
+      uint32_t raw[16], work[16];              // single chunk body, see run_epilogue_t
       __syncwarp();
-      tmem_ld16_issue(taddr + ch0 * 16, rawA);
+      tmem_ld16_issue(taddr + ch0 * 16, raw);
 #pragma unroll 1
-      for (int c = 0; c < chn; c += 2) {
+      for (int c = 0; c < chn; ++c) {
         tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) work[j] = raw[j];
         __syncwarp();
-        if (c + 1 < chn) tmem_ld16_issue(taddr + (ch0 + c + 1) * 16, rawB);
-        process(c, rawA);
-        if (c + 1 >= chn) break;
-        tmem_ld_wait();
-        __syncwarp();
-        if (c + 2 < chn) tmem_ld16_issue(taddr + (ch0 + c + 2) * 16, rawA);
-        process(c + 1, rawB);
+        if (c + 1 < chn) tmem_ld16_issue(taddr + (ch0 + c + 1) * 16, raw);
+        process(c, work);
       }
       if (ch0 + 4 >= c_hi) {              // last TMEM read of this item: hand the accumulator back before the copy-out
         tc_fence_before();
@@ -1189,13 +1199,33 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         tc_fence_after();
         const uint32_t a_unit = a_base + ia * p.a_unit_bytes;
         if (!(p.dbg & 1)) {
+          // descriptors as 32-bit halves: high words constant, low words = start address >> 4 (+ LBO bit 16)
+          constexpr uint32_t a_hi = ((uint32_t)(BWX * 128) >> 4) | (1u << 14) | (2u << 29);
+          constexpr uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+          const uint32_t a_lo0 = ((a_unit & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t bs16 = (uint32_t)p.b_stage_bytes >> 4;
+          uint32_t b_lo = (((w_base + (uint32_t)(kbt * TAPS) * (uint32_t)p.b_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          if (it == 0) {                                   // first tile only: the weights of this K block have landed
+            for (int wb = 0; wb < TAPS / WG; ++wb) mbar_wait(wfull0 + 8 * (kbt * (TAPS / WG) + wb), 0);
+            tc_fence_after();
+          }
+          // one fully unrolled instance per K-slice count (the tail K block of C = 112 has 3 slices, SPyNet 1 or 2)
+          auto issue_block = [&](auto nk_c) {
+            constexpr int NK = decltype(nk_c)::value;
 #pragma unroll
-          for (int tap = 0; tap < TAPS; ++tap) {
-            if (it == 0 && tap % WG == 0) { mbar_wait(wfull0 + 8 * ((kbt * TAPS + tap) / WG), 0); tc_fence_after(); }     // weights have landed (first tile only)
-            const uint64_t ad = smem_desc_sw128_sbo(a_unit + (uint32_t)((tap / RR) * BWX + (tap % RR)) * 128u, (uint32_t)BWX * 128u);
-            const uint64_t bd = smem_desc_sw128(w_base + (kbt * TAPS + tap) * p.b_stage_bytes);
-            for (int ks = 0; ks < nks; ++ks)
-              umma_f16_2sm_if(issue, d_tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)((tap | ks) > 0));
+            for (int tap = 0; tap < TAPS; ++tap) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)((tap / RR) * BWX + (tap % RR)) * 8u;
+#pragma unroll
+              for (int ks = 0; ks < NK; ++ks)
+                umma_f16_2sm_if_lh(issue, d_tmem, a_lo + 2u * ks, a_hi, b_lo + 2u * ks, b_hi, idesc, accumulate | (uint32_t)((tap | ks) > 0));
+              b_lo += bs16;
+            }
+          };
+          switch (nks) {
+            case 4: issue_block(std::integral_constant<int, 4>{}); break;
+            case 3: issue_block(std::integral_constant<int, 3>{}); break;
+            case 2: issue_block(std::integral_constant<int, 2>{}); break;
+            default: issue_block(std::integral_constant<int, 1>{}); break;
           }
         }
         umma_commit_2sm_if(issue, aempty0 + 8 * ia, (uint16_t)3);

@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'vmgb.h')
-LIB_PATH = os.path.join(_HERE, 'libvmgb.so')
+LIB_PATH = os.environ.get('VMGB_LIB') or os.path.join(_HERE, 'libvmgb.so')      # VMGB_LIB: A/B builds (tools only)
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
