@@ -35,6 +35,7 @@ struct TcP {
   int out_smem;                                // bytes of the output staging tile [128][NT+8] bf16 (0 = direct stores)
   int aux_smem;                                // bytes of the gate-operand staging buffer (GATE epilogue; 0 = off)
   int wst;                                     // 1 = warp-private transposition staging epilogue (run_epilogue_w), 32 KB
+  int res_tma;                                 // 1 = residual tile fetched by TMA one item ahead (run_epilogue_rtma, CTA-pair kernel)
   int dbg;                                     // bottleneck probes (tools/microbench.py): 1 = no MMA, 2 = no drain, 4 = no activation loads
 };
 
@@ -744,6 +745,92 @@ __device__ __forceinline__ void run_epilogue_w(const TcP& p, float* bias_s, uint
   run_epilogue_w_t<-1, -1>(p, bias_s, tmem_base, tfull0, tempty0, first, step, total, warp, lane, origin, tempty_cluster0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Residual-add epilogue with the residual tile fetched by TMA (CTA-pair kernel, resblock conv2: act = none, bf16 in/out).
+// The per-thread cp.async staging of run_epilogue_t costs ~1.2 us of LSU / address work per 128 x 112 tile - as much as
+// the MMAs of the tile.  Here one elected thread issues a single 4-D box {NT channels, 8 cols, 16 rows} of the residual
+// tensor per tile (row r of the accumulator = row r of the box, NT*2 bytes apart, TMA zero-fills the image overhang), one
+// item ahead: the box of item t+1 is requested as soon as every epilogue thread has read item t and lands while the
+// MMAs of t+1 run.  Epilogue threads only do ld.shared + FMA + store.
+// ---------------------------------------------------------------------------------------------
+template <class Origin>
+__device__ __forceinline__ void run_epilogue_rtma(const TcP& p, float* bias_s, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                                  uint32_t rfull, const CUtensorMap* mapR, long long first, long long step, long long total,
+                                                  int warp, int lane, Origin origin, uint32_t tempty_cluster0) {
+  const int ew = warp - 4, quarter = warp & 3, half = ew >> 2;
+  const int row = quarter * 32 + lane;
+  const int nchunks = p.NT >> 4;
+  const uint32_t res_s = (smem_u32(bias_s) + 1024u + 127u) & ~127u;
+  const uint32_t row_bytes = (uint32_t)p.NT * 2u;
+  const int bw_shift = 31 - __clz(p.BW), bw_mask = p.BW - 1;
+  uint32_t acc_phase0 = 0, acc_phase1 = 0, rphase = 0;
+  int it = 0, bias_combo = -1;
+  const bool issuer_warp = ew == 0;
+  auto request = [&](long long t) {             // whole warp 4 calls, one lane issues
+    int combo, img, h0, w0; bool tvalid;
+    origin(t, combo, img, h0, w0, tvalid);
+    const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+    if (elect_one()) {
+      mbar_expect_tx(rfull, 128u * row_bytes);
+      tma_load_4d(res_s, mapR, rfull, g * p.Cout_g + nt * p.NT, w0, h0, tvalid ? img : p.n_img);
+    }
+    __syncwarp();
+  };
+  if (issuer_warp && first < total) request(first);
+  for (long long t = first; t < total; t += step, ++it) {
+    const int as = it & 1;
+    int combo, img, h0, w0; bool tvalid;
+    origin(t, combo, img, h0, w0, tvalid);
+    const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+    const int hh = h0 + (row >> bw_shift), ww = w0 + (row & bw_mask);
+    const bool pvalid = tvalid && hh < p.H && ww < p.W;
+    const long long pix = ((long long)img * p.H + hh) * p.W + ww;
+    const uint32_t aph = as ? acc_phase1 : acc_phase0;
+    if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_STRIDE;
+    if (combo != bias_combo) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int c = ew * 32 + lane; c < p.NT; c += 256) {
+        const int nb = nt * p.NT + c;
+        bias_s[c] = (p.bias && nb < p.Cout_g) ? __ldg(p.bias + g * p.Cout_g + nb) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      bias_combo = combo;
+    }
+    mbar_wait(rfull, rphase);                    // residual box of this item
+    rphase ^= 1;
+    mbar_wait(tfull0 + 8 * as, aph);
+    tc_fence_after();
+    if (!(p.dbg & 2)) {
+      const uint32_t rrow = res_s + (uint32_t)row * row_bytes;
+      uint32_t raw[16], work[16];
+      int ch = half;
+      __syncwarp();
+      if (ch < nchunks) tmem_ld16_issue(taddr + ch * 16, raw);
+#pragma unroll 1
+      while (ch < nchunks) {
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) work[j] = raw[j];
+        __syncwarp();
+        if (ch + 2 < nchunks) tmem_ld16_issue(taddr + (ch + 2) * 16, raw);
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+        const bool hp = pvalid && nt * p.NT + ch * 16 + 16 <= p.Cout_g;
+        if (hp) {
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(rrow + ch * 32) : "memory");
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(rrow + ch * 32 + 16) : "memory");
+        }
+        epilogue_chunk<VMGB_ACT_NONE, VMGB_EPI_RESADD, 0>(p, work, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, r0, r1);
+        ch += 2;
+      }
+    }
+    tc_fence_before();
+    if (tempty_cluster0) mbar_arrive_cluster(tempty_cluster0 + 8 * as); else mbar_arrive(tempty0 + 8 * as);
+    asm volatile("bar.sync 1, 256;" ::: "memory");      // every thread has read this item's residual: the buffer can be refilled
+    if (issuer_warp && t + step < total) request(t + step);
+  }
+}
+
 constexpr int TC_THREADS = 384;      // warps 0-3: producer / MMA / TMEM alloc / spare ; warps 4-11: epilogue
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -1088,7 +1175,8 @@ constexpr int WS2_MAX_BOXES = 36;      // weight barriers: 9 taps x up to 4 K bl
 template <int RR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB, const TcP p) {
+                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
+                   const __grid_constant__ CUtensorMap mapR, const TcP p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr int BWX = 8 + RR - 1, TAPS = RR * RR, UROWS = 16 + RR - 1, PADR = RR / 2;
@@ -1103,7 +1191,8 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   const uint32_t afull0 = bar_base, aempty0 = afull0 + 8 * p.ra;
   const uint32_t wfull0 = aempty0 + 8 * p.ra;          // one barrier per weight box (<= 36): the first tile starts on tap 0's weights
   const uint32_t tfull0 = wfull0 + 8 * WS2_MAX_BOXES, tempty0 = tfull0 + 16;
-  const uint32_t tmem_slot = tempty0 + 16;
+  const uint32_t rfull = tempty0 + 16;                 // residual box of the next item (run_epilogue_rtma)
+  const uint32_t tmem_slot = rfull + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -1113,6 +1202,7 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
     for (int i = 0; i < p.ra; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
     for (int i = 0; i < nboxes / WG; ++i) mbar_init(wfull0 + 8 * i, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 512); }
+    mbar_init(rfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -1238,7 +1328,18 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps per CTA, each CTA drains its own 128 accumulator rows) =====================
     pdl_wait();                        // residual reads and output writes wait for the predecessors
-    if (p.wst)
+    if (p.res_tma)
+      run_epilogue_rtma(p, bias_s, tmem_base, tfull0, tempty0, rfull, &mapR, first, step, n_pairs, warp, lane,
+                        [&](long long t, int& cmb, int& img, int& h0, int& w0, bool& valid) {
+                          const long long mt = 2 * t + rank;
+                          cmb = combo;
+                          valid = mt < n_mt;
+                          img = valid ? (int)(mt / tiles_per_img) : 0;
+                          const int rem = valid ? (int)(mt % tiles_per_img) : 0;
+                          h0 = (rem / p.tiles_w) * 16; w0 = (rem % p.tiles_w) * 8;
+                        },
+                        mapa_rank(tempty0, 0));
+    else if (p.wst)
       run_epilogue_w(p, bias_s, tmem_base, tfull0, tempty0, first, step, n_pairs, warp, lane,
                      [&](long long t, int& cmb, int& img, int& h0, int& w0, bool& valid) {
                        const long long mt = 2 * t + rank;
@@ -1283,6 +1384,7 @@ static int g_num_sms = 0;
 static int g_smem_optin = 0;
 static std::once_flag g_once;
 static int g_pdl = 1;         // VMGB_PDL=0 turns programmatic dependent launch off
+static int g_res_tma = 1;     // VMGB_RES_TMA=0: residual of the pair kernel by per-thread cp.async instead of TMA (A/B switch)
 static int g_ws2_multi = 1;   // VMGB_WS2_MULTI=0: multi-source convs stay on the per-tap kernel (A/B switch)
 static int g_wst_gate = 1;    // VMGB_WST_GATE=0: gate epilogue on the per-thread staging path (A/B switch)
 static int g_no_wst = 0;      // VMGB_NO_WST=1: A/B switch (tools/microbench.py) for the warp-private staging epilogue
@@ -1295,6 +1397,7 @@ static void tc_init() {
   if (const char* e = getenv("VMGB_NO_WST")) g_no_wst = atoi(e);
   if (const char* e = getenv("VMGB_PDL")) g_pdl = atoi(e);
   if (const char* e = getenv("VMGB_WS2_MULTI")) g_ws2_multi = atoi(e);
+  if (const char* e = getenv("VMGB_RES_TMA")) g_res_tma = atoi(e);
   if (const char* e = getenv("VMGB_WST_GATE")) g_wst_gate = atoi(e);      // A/B switch for tools/microbench.py
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1371,7 +1474,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   p.bias = (const float*)bias; p.out = out; p.res = res; p.aux = aux;
   p.out_dt = out_dt; p.out_pitch = out_pitch; p.res_dt = res_dt; p.res_pitch = res_pitch; p.aux_dt = aux_dt; p.aux_pitch = aux_pitch;
   p.act = act; p.alpha = act_alpha; p.out_scale = out_scale; p.epi = epi; p.res_scale = res_scale; p.ps = pixel_shuffle;
-  p.dbg = 0; p.wst = 0;
+  p.dbg = 0; p.wst = 0; p.res_tma = 0;
   p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0; p.res_smem = 0; p.out_smem = 0; p.aux_smem = 0;
   const int budget = g_smem_optin - 1024 - 512 - 1024;     // alignment slack, barriers, bias staging
 
@@ -1414,7 +1517,18 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       p.BH = 16; p.BW = 8; p.a_unit_bytes = ubytes; p.stages = 0;
       p.tiles_h = (H + 15) / 16; p.tiles_w = (W + 7) / 8;
       p.total_tiles = n_mt * groups * p.nt_per_g;
-      CUtensorMap mA[3], mB;
+      CUtensorMap mA[3], mB, mR;
+      // resblock conv2 (no activation, bf16 residual and output): the residual tile comes by TMA into the same 128 x NT
+      // staging buffer the cp.async path would use
+      p.res_tma = g_res_tma && !best_wst && best_res > 0 && epi == VMGB_EPI_RESADD && act == VMGB_ACT_NONE && groups == 1 &&
+                  out_dt == VMGB_BF16 && res_dt == VMGB_BF16 && pixel_shuffle == 0 && (Cout_g & 15) == 0 && (res_pitch & 7) == 0 &&
+                  (out_pitch & 7) == 0 && !(reinterpret_cast<uintptr_t>(res) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15) && best_nt <= 256;
+      if (p.res_tma) {
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+        cuuint64_t str[3] = {(cuuint64_t)res_pitch * 2, (cuuint64_t)W * res_pitch * 2, (cuuint64_t)H * W * res_pitch * 2};
+        cuuint32_t box[4] = {(cuuint32_t)best_nt, 8, 16, 1};
+        if (!encode_bf16(&mR, res, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) p.res_tma = 0;
+      }
       {
         const void* srcs[3] = {x, x1, x2};
         const int c_extent = n_src > 1 ? p.Cs : Cin;
@@ -1434,15 +1548,17 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
         if (!encode_bf16(&mB, w, 2, dims, str, box)) return VMGB_EINVAL;
       }
       long long per = n_pairs < clusters_max ? n_pairs : clusters_max;
-      const int smem = p.ra * p.a_unit_bytes + (nboxes * p.b_stage_bytes + 1023) / 1024 * 1024 + 1024 + 512 + 1024 + best_res + p.out_smem;
+      const int smem = p.ra * p.a_unit_bytes + (nboxes * p.b_stage_bytes + 1023) / 1024 * 1024 + 1024 + 512 + 1024 + best_res + p.out_smem +
+                       (p.res_tma ? 256 : 0);
+      if (!p.res_tma) mR = mB;            // unused, but a valid descriptor
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)(2 * per * groups * best_slices)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
       cudaLaunchAttribute at[2];
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
-      cudaError_t e = R == 3 ? cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel<3>, mA[0], mA[1], mA[2], mB, p)
-                             : cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel<7>, mA[0], mA[1], mA[2], mB, p);
+      cudaError_t e = R == 3 ? cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel<3>, mA[0], mA[1], mA[2], mB, mR, p)
+                             : cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel<7>, mA[0], mA[1], mA[2], mB, mR, p);
       if (e != cudaSuccess) { g_last_cuda_error = (int)e; return VMGB_ECUDA; }
       return check_launch();
     }
@@ -1485,7 +1601,18 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       p.BH = 16; p.BW = 8; p.a_unit_bytes = ubytes; p.stages = 0;
       p.tiles_h = (H + 15) / 16; p.tiles_w = (W + 7) / 8;
       p.total_tiles = n_mt * groups * p.nt_per_g;
-      CUtensorMap mA[3], mB;
+      CUtensorMap mA[3], mB, mR;
+      // resblock conv2 (no activation, bf16 residual and output): the residual tile comes by TMA into the same 128 x NT
+      // staging buffer the cp.async path would use
+      p.res_tma = g_res_tma && !best_wst && best_res > 0 && epi == VMGB_EPI_RESADD && act == VMGB_ACT_NONE && groups == 1 &&
+                  out_dt == VMGB_BF16 && res_dt == VMGB_BF16 && pixel_shuffle == 0 && (Cout_g & 15) == 0 && (res_pitch & 7) == 0 &&
+                  (out_pitch & 7) == 0 && !(reinterpret_cast<uintptr_t>(res) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15) && best_nt <= 256;
+      if (p.res_tma) {
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+        cuuint64_t str[3] = {(cuuint64_t)res_pitch * 2, (cuuint64_t)W * res_pitch * 2, (cuuint64_t)H * W * res_pitch * 2};
+        cuuint32_t box[4] = {(cuuint32_t)best_nt, 8, 16, 1};
+        if (!encode_bf16(&mR, res, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) p.res_tma = 0;
+      }
       const void* srcs[3] = {x, x1, x2};
       const int c_extent = n_src > 1 ? p.Cs : Cin;
       for (int s = 0; s < 3; ++s) {
