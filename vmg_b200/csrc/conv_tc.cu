@@ -799,12 +799,26 @@ __device__ __forceinline__ void run_epilogue_rtma(const TcP& p, float* bias_s, u
     }
     mbar_wait(rfull, rphase);                    // residual box of this item
     rphase ^= 1;
+    // the thread's residual pieces move to registers BEFORE the accumulator is awaited, so that the box of the next item
+    // can be requested now and lands while this item is drained (host: NT <= 128, i.e. <= 4 chunks per thread)
+    const uint32_t rrow = res_s + (uint32_t)row * row_bytes;
+    uint4 rr[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ch = half + 2 * i;
+      rr[i][0] = make_uint4(0, 0, 0, 0); rr[i][1] = rr[i][0];
+      if (ch < nchunks) {
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[i][0].x), "=r"(rr[i][0].y), "=r"(rr[i][0].z), "=r"(rr[i][0].w) : "r"(rrow + ch * 32) : "memory");
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[i][1].x), "=r"(rr[i][1].y), "=r"(rr[i][1].z), "=r"(rr[i][1].w) : "r"(rrow + ch * 32 + 16) : "memory");
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");      // every thread holds its residual: the buffer can be refilled
+    if (issuer_warp && t + step < total) request(t + step);
     mbar_wait(tfull0 + 8 * as, aph);
     tc_fence_after();
     if (!(p.dbg & 2)) {
-      const uint32_t rrow = res_s + (uint32_t)row * row_bytes;
       uint32_t raw[16], work[16];
-      int ch = half;
+      int ch = half, i = 0;
       __syncwarp();
       if (ch < nchunks) tmem_ld16_issue(taddr + ch * 16, raw);
 #pragma unroll 1
@@ -814,20 +828,15 @@ __device__ __forceinline__ void run_epilogue_rtma(const TcP& p, float* bias_s, u
         for (int j = 0; j < 16; ++j) work[j] = raw[j];
         __syncwarp();
         if (ch + 2 < nchunks) tmem_ld16_issue(taddr + (ch + 2) * 16, raw);
-        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+        const uint4 r0 = i == 0 ? rr[0][0] : (i == 1 ? rr[1][0] : (i == 2 ? rr[2][0] : rr[3][0]));
+        const uint4 r1 = i == 0 ? rr[0][1] : (i == 1 ? rr[1][1] : (i == 2 ? rr[2][1] : rr[3][1]));
         const bool hp = pvalid && nt * p.NT + ch * 16 + 16 <= p.Cout_g;
-        if (hp) {
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(rrow + ch * 32) : "memory");
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(rrow + ch * 32 + 16) : "memory");
-        }
         epilogue_chunk<VMGB_ACT_NONE, VMGB_EPI_RESADD, 0>(p, work, pvalid, img, hh, ww, pix, g, nt, ch, bias_s, hp, r0, r1);
-        ch += 2;
+        ch += 2; ++i;
       }
     }
     tc_fence_before();
     if (tempty_cluster0) mbar_arrive_cluster(tempty_cluster0 + 8 * as); else mbar_arrive(tempty0 + 8 * as);
-    asm volatile("bar.sync 1, 256;" ::: "memory");      // every thread has read this item's residual: the buffer can be refilled
-    if (issuer_warp && t + step < total) request(t + step);
   }
 }
 
@@ -1522,7 +1531,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       // staging buffer the cp.async path would use
       p.res_tma = g_res_tma && !best_wst && best_res > 0 && epi == VMGB_EPI_RESADD && act == VMGB_ACT_NONE && groups == 1 &&
                   out_dt == VMGB_BF16 && res_dt == VMGB_BF16 && pixel_shuffle == 0 && (Cout_g & 15) == 0 && (res_pitch & 7) == 0 &&
-                  (out_pitch & 7) == 0 && !(reinterpret_cast<uintptr_t>(res) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15) && best_nt <= 256;
+                  (out_pitch & 7) == 0 && !(reinterpret_cast<uintptr_t>(res) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15) && best_nt <= 128;
       if (p.res_tma) {
         cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
         cuuint64_t str[3] = {(cuuint64_t)res_pitch * 2, (cuuint64_t)W * res_pitch * 2, (cuuint64_t)H * W * res_pitch * 2};
@@ -1606,7 +1615,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       // staging buffer the cp.async path would use
       p.res_tma = g_res_tma && !best_wst && best_res > 0 && epi == VMGB_EPI_RESADD && act == VMGB_ACT_NONE && groups == 1 &&
                   out_dt == VMGB_BF16 && res_dt == VMGB_BF16 && pixel_shuffle == 0 && (Cout_g & 15) == 0 && (res_pitch & 7) == 0 &&
-                  (out_pitch & 7) == 0 && !(reinterpret_cast<uintptr_t>(res) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15) && best_nt <= 256;
+                  (out_pitch & 7) == 0 && !(reinterpret_cast<uintptr_t>(res) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15) && best_nt <= 128;
       if (p.res_tma) {
         cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
         cuuint64_t str[3] = {(cuuint64_t)res_pitch * 2, (cuuint64_t)W * res_pitch * 2, (cuuint64_t)H * W * res_pitch * 2};
