@@ -79,6 +79,9 @@ TC = [c for c in GENERIC if c[3] >= 16] + [
     (1, 1, 1000, 1344, 224, 1, 1, ops.ACT_NONE, ops.EPI_RESADD, 0, 1), # FFN fc2, long K
     (1, 16, 16, 224, 1344, 3, 4, ops.ACT_GELU, ops.EPI_STORE, 0, 1),   # grouped, Cout_g=336 (2 N tiles of 176)
     (1, 1, 130, 896, 224, 1, 1, ops.ACT_NONE, ops.EPI_STORE, 0, 1),    # downsample linear
+    (1, 1, 333, 224, 224, 1, 1, ops.ACT_NONE, ops.EPI_GATE, 0, 1),     # level-1 proj + gate: N = 224 split in 2 tiles of 112
+    (1, 1, 333, 224, 224, 1, 1, ops.ACT_NONE, ops.EPI_RESADD, 0, 1),   # the same with a residual epilogue
+    (1, 1, 333, 144, 288, 1, 1, ops.ACT_NONE, ops.EPI_RESADD, 0, 1),   # N = 288 stays in two 144-column tiles (old path)
     (1, 1, 130, 36, 144, 1, 1, ops.ACT_NONE, ops.EPI_STORE, 0, 1),     # upsample linear, K=36 (pitch not 16B multiple -> generic)
     (4, 16, 16, 144, 576, 3, 1, ops.ACT_LRELU, ops.EPI_STORE, 2, 1),   # upconv1 + PS, 3 N tiles
     (2, 24, 24, 8, 32, 7, 1, ops.ACT_RELU, ops.EPI_STORE, 0, 1),       # SPyNet 7x7, Cin=8 (49 taps, 1 K step each)

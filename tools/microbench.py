@@ -46,6 +46,7 @@ def conv_cases():
         ('ffn_fc2_672to112', 1, 1, 25 * 184 * 320, 672, 112, 1, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
         ('linear_112', 1, 1, 25 * 184 * 320, 112, 112, 1, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
         ('gate_proj_112', 1, 1, 25 * 184 * 320, 112, 112, 1, 1, 1, ops.EPI_GATE, ops.ACT_NONE, 0),
+        ('gate_proj_224', 1, 1, 25 * 92 * 160, 224, 224, 1, 1, 1, ops.EPI_GATE, ops.ACT_NONE, 0),
         ('linear_448', 1, 1, 100 * 23 * 40, 448, 448, 1, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
         ('upconv2_112to256_ps', 4, 360, 640, 112, 256, 3, 1, 1, ops.EPI_STORE, ops.ACT_LRELU, 2),
         ('hrconv_64', 2, 720, 1280, 64, 64, 3, 1, 1, ops.EPI_STORE, ops.ACT_LRELU, 0),

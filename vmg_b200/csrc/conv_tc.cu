@@ -1393,6 +1393,7 @@ static int g_num_sms = 0;
 static int g_smem_optin = 0;
 static std::once_flag g_once;
 static int g_pdl = 1;         // VMGB_PDL=0 turns programmatic dependent launch off
+static int g_split_n = 1;     // VMGB_SPLIT_N=0: keep N <= 256 linears in one N tile (A/B switch)
 static int g_res_tma = 1;     // VMGB_RES_TMA=0: residual of the pair kernel by per-thread cp.async instead of TMA (A/B switch)
 static int g_ws2_multi = 1;   // VMGB_WS2_MULTI=0: multi-source convs stay on the per-tap kernel (A/B switch)
 static int g_wst_gate = 1;    // VMGB_WST_GATE=0: gate epilogue on the per-thread staging path (A/B switch)
@@ -1407,6 +1408,7 @@ static void tc_init() {
   if (const char* e = getenv("VMGB_PDL")) g_pdl = atoi(e);
   if (const char* e = getenv("VMGB_WS2_MULTI")) g_ws2_multi = atoi(e);
   if (const char* e = getenv("VMGB_RES_TMA")) g_res_tma = atoi(e);
+  if (const char* e = getenv("VMGB_SPLIT_N")) g_split_n = atoi(e);
   if (const char* e = getenv("VMGB_WST_GATE")) g_wst_gate = atoi(e);      // A/B switch for tools/microbench.py
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1474,6 +1476,10 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   p.n_img = n_img; p.H = H; p.W = W; p.Cin_g = Cin_g; p.Cout_g = Cout_g; p.groups = groups; p.R = R; p.S = S; p.n_src = n_src;
   p.Cs = n_src > 1 ? Cin / n_src : Cin_g;
   p.nt_per_g = (Cout_g + 255) / 256;
+  // HBM-bound 1x1 layers with a residual / gate epilogue and 128 < N <= 256 (level-1 proj and fc2-like linears): two N
+  // tiles of <= 128 columns keep them on the coalesced warp-private staging epilogue (one pass per warp); the second
+  // read of the activations comes from L2
+  if (R == 1 && S == 1 && epi != VMGB_EPI_STORE && g_split_n && Cout_g > 128 && Cout_g <= 256 && (Cout_g & 31) == 0 && Cin <= 256) p.nt_per_g = 2;
   p.NT = (((Cout_g + p.nt_per_g - 1) / p.nt_per_g) + 15) / 16 * 16;
   int max_koff = 0;
   for (int g = 0; g < groups; ++g) max_koff = max(max_koff, (g * Cin_g) & 7);
