@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128) ltam_wins_kernel(const void* q, const voi
 // across key frames) and every (head, query) thread then reads its head segment from shared memory.  The
 // direct version above issues 8-byte loads per thread and re-reads each row through L1 for the 4 queries.
 // ---------------------------------------------------------------------------------------------
-constexpr int LTAM_STAGES = 4;
+constexpr int LTAM_STAGES = 3;      // measured: 3 stages (47 KB, 4 blocks per SM) beat 4 stages (62 KB, 3 blocks) by ~8 %
 template <int D4>
 __global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ keys,
                                                              const __nv_bfloat16* __restrict__ vals, long long kv_stride,
