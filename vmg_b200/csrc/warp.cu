@@ -50,6 +50,54 @@ __global__ void flow_warp_bilinear_kernel(const void* x, int x_dt, int x_pitch, 
   }
 }
 
+// bf16 fast path: one thread per (pixel, 8 channels), 16-byte loads and stores (same tap order and fp32 accumulation as the
+// generic kernel above, so the results are bit-identical); half the threads and half the redundant coordinate work
+__global__ void __launch_bounds__(256) flow_warp_bilinear8_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch, const float* __restrict__ flow,
+                                                                 __nv_bfloat16* __restrict__ out, int out_pitch, int n, int h, int w, int C,
+                                                                 long long total) {
+  const int C8 = C >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8); const long long pix = i / C8;
+    const int px = (int)(pix % w); const long long t = pix / w; const int py = (int)(t % h); const int img = (int)(t / h);
+    const float2 f = *reinterpret_cast<const float2*>(flow + pix * 2);
+    const float ix = warp_coord((float)px, f.x, w), iy = warp_coord((float)py, f.y, h);
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+    const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix, wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
+    const long long ib = (long long)img * h;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const int ys[4] = {y0, y0, y1, y1}, xs[4] = {x0, x1, x0, x1};
+    const float ws[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
+    uint4 v[4];
+    bool ok[4];
+#pragma unroll
+    for (int tp = 0; tp < 4; ++tp) {
+      ok[tp] = ys[tp] >= 0 && ys[tp] < h && xs[tp] >= 0 && xs[tp] < w;
+      v[tp] = ok[tp] ? __ldg(reinterpret_cast<const uint4*>(x + ((ib + ys[tp]) * w + xs[tp]) * x_pitch + c8 * 8)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int tp = 0; tp < 4; ++tp) {
+      if (ok[tp]) {
+        const uint32_t wd[4] = {v[tp].x, v[tp].y, v[tp].z, v[tp].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc[2 * q] += __uint_as_float(wd[q] << 16) * ws[tp];
+          acc[2 * q + 1] += __uint_as_float(wd[q] & 0xffff0000u) * ws[tp];
+        }
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+      o[q] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(out + pix * out_pitch + c8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // location warp: nearest, border (locations stay exact in-range integers)
 __global__ void flow_warp_nearest_kernel(const float* __restrict__ loc, int in_pitch, const float* __restrict__ flow,
                                          float* __restrict__ out, int out_pitch, int n, int h, int w, int K2, long long total) {
@@ -235,6 +283,13 @@ using namespace vmgb;
 extern "C" int vmgb_flow_warp_bilinear(const void* x, int x_dt, int x_pitch, const float* flow, void* out, int out_dt, int out_pitch,
                                        int n, int h, int w, int C, void* stream) {
   if (!x || !flow || !out || !dt_ok(x_dt) || !dt_ok(out_dt) || (C & 3) || (x_pitch & 3) || (out_pitch & 3)) return VMGB_EINVAL;
+  if (x_dt == VMGB_BF16 && out_dt == VMGB_BF16 && (C & 7) == 0 && (x_pitch & 7) == 0 && (out_pitch & 7) == 0 &&
+      !(((uintptr_t)x | (uintptr_t)out) & 15)) {
+    const long long total8 = (long long)n * h * w * (C / 8);
+    flow_warp_bilinear8_kernel<<<grid_for2(total8, 256, 148 * 32), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, x_pitch, flow,
+                                                                                                 (__nv_bfloat16*)out, out_pitch, n, h, w, C, total8);
+    return check_launch();
+  }
   long long total = (long long)n * h * w * (C / 4);
   flow_warp_bilinear_kernel<<<grid_for2(total, 256, 148 * 32), 256, 0, as_stream(stream)>>>(x, x_dt, x_pitch, flow, out, out_dt, out_pitch, n, h, w, C, total);
   return check_launch();
