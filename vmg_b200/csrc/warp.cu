@@ -110,6 +110,20 @@ __global__ void flow_warp_nearest_kernel(const float* __restrict__ loc, int in_p
   }
 }
 
+// one thread per (pixel, tracked location = 2 floats): half the threads and coordinate work of the scalar kernel
+__global__ void __launch_bounds__(256) flow_warp_nearest2_kernel(const float* __restrict__ loc, int in_pitch, const float* __restrict__ flow,
+                                                                float* __restrict__ out, int out_pitch, int n, int h, int w, int K,
+                                                                long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K); const long long pix = i / K;
+    const int px = (int)(pix % w); const long long t = pix / w; const int py = (int)(t % h); const int img = (int)(t / h);
+    const float2 f = *reinterpret_cast<const float2*>(flow + pix * 2);
+    const int sx = (int)rintf(warp_coord((float)px, f.x, w)), sy = (int)rintf(warp_coord((float)py, f.y, h));
+    *reinterpret_cast<float2*>(out + pix * out_pitch + 2 * k) =
+        *reinterpret_cast<const float2*>(loc + (((long long)img * h + sy) * w + sx) * in_pitch + 2 * k);
+  }
+}
+
 __global__ void loc_identity_kernel(float* __restrict__ loc, int pitch, int c0, int n, int h, int w, long long total) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int px = (int)(i % w); const int py = (int)((i / w) % h);
@@ -298,6 +312,11 @@ extern "C" int vmgb_flow_warp_bilinear(const void* x, int x_dt, int x_pitch, con
 extern "C" int vmgb_flow_warp_nearest(const float* loc, int in_pitch, const float* flow, float* out, int out_pitch, int n, int h,
                                       int w, int K2, void* stream) {
   if (!loc || !flow || !out || K2 <= 0 || loc == out) return VMGB_EINVAL;
+  if (!(K2 & 1) && !(in_pitch & 1) && !(out_pitch & 1) && !(((uintptr_t)loc | (uintptr_t)out) & 7)) {
+    const long long total2 = (long long)n * h * w * (K2 / 2);
+    flow_warp_nearest2_kernel<<<grid_for2(total2, 256, 148 * 32), 256, 0, as_stream(stream)>>>(loc, in_pitch, flow, out, out_pitch, n, h, w, K2 / 2, total2);
+    return check_launch();
+  }
   long long total = (long long)n * h * w * K2;
   flow_warp_nearest_kernel<<<grid_for2(total, 256, 148 * 32), 256, 0, as_stream(stream)>>>(loc, in_pitch, flow, out, out_pitch, n, h, w, K2, total);
   return check_launch();
