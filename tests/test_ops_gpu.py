@@ -108,6 +108,7 @@ C3 = [
     (1, 16, 16, 224, 1344, 3, 4, ops.ACT_GELU, ops.EPI_STORE, 0, 1),    # grouped, 2 N tiles
     (4, 16, 16, 144, 576, 3, 1, ops.ACT_LRELU, ops.EPI_STORE, 2, 1),    # 3 N tiles + pixel shuffle
     (3, 64, 48, 112, 112, 3, 1, ops.ACT_NONE, ops.EPI_RESADD, 0, 1),    # several tiles per CTA: ring wrap-around
+    (2, 40, 41, 144, 144, 3, 1, ops.ACT_NONE, ops.EPI_RESADD, 0, 1),    # few_levels resblock conv2: two N slices of 80, TMA residual, odd tile count
 ]
 
 
