@@ -50,6 +50,14 @@ extern "C" {
 #define VMGB_EPI_RESADD 1
 #define VMGB_EPI_GATE   2
 
+/* whose fp32 rounding the flow_warp coordinate normalisation `2*g / max(size-1, 1) - 1` (trajectory.py:101-106)
+ * follows: ATen's CPU div kernel divides; ATen's CUDA div kernel multiplies by the fp32 reciprocal of a Python-scalar
+ * divisor.  The two differ by one ulp now and then, which matters only to the NEAREST warp of the tracked locations
+ * (a coordinate that lands on an exact .5 tie).  The model defaults to the CUDA order (what the reference's own
+ * GPU forward computes); tests against CPU-minted goldens select the CPU order. */
+#define VMGB_COORD_ATEN_CPU  0
+#define VMGB_COORD_ATEN_CUDA 1
+
 int         vmgb_version(void);
 const char* vmgb_arch(void);                 /* "sm_100a" */
 int         vmgb_last_cuda_error(void);      /* last cudaError_t seen by this library */
@@ -149,9 +157,15 @@ int vmgb_decay_weights(float* w, const float* gamma, long long n, void* stream);
  * feature warp: bilinear; x,out [n,h,w,C]; flow fp32 [n,h,w,2] (dx,dy).
  * location warp: nearest; loc fp32 [n,h,w,2*K] in, [n,h,w,(out_pitch)] out, `K2` = 2*K channels moved. */
 int vmgb_flow_warp_bilinear(const void* x, int x_dt, int x_pitch, const float* flow, void* out, int out_dt, int out_pitch,
-                            int n, int h, int w, int C, void* stream);
+                            int n, int h, int w, int C, int semantics, void* stream);
 int vmgb_flow_warp_nearest(const float* loc, int in_pitch, const float* flow, float* out, int out_pitch,
-                           int n, int h, int w, int K2, void* stream);
+                           int n, int h, int w, int K2, int semantics, void* stream);
+/* flow_warp_fused: both warps of one trajectory step (trajectory.py:330-333 / 410-430: feat_prop bilinear, all 2K
+ * location channels nearest, same flow) in ONE launch; bf16 features with C % 8 == 0 and 16-byte aligned rows,
+ * K2 even; returns VMGB_EUNSUPPORTED otherwise (the caller then issues the two launches above). */
+int vmgb_flow_warp_fused(const void* x, int x_pitch, const float* flow, void* out, int out_pitch,
+                         const float* loc, int loc_in_pitch, float* loc_out, int loc_out_pitch, int K2,
+                         int n, int h, int w, int C, int semantics, void* stream);
 /* writes the identity grid (x, y) into channels [c0, c0+2) of loc [n,h,w,pitch] (trajectory.py:316-317,365) */
 int vmgb_loc_identity(float* loc, int pitch, int c0, int n, int h, int w, void* stream);
 
@@ -200,7 +214,7 @@ int vmgb_avgpool2(const float* x, float* out, int n, int H, int W, int C, void* 
  * flow_up = 2*bilinear_x2(flow_coarse [pairs,h/2,w/2,2], align_corners=True) (zeros when NULL);
  * out8 [pairs,h,w,8] = cat[ref, warp_border(supp, flow_up), flow_up]; flow_up [pairs,h,w,2] also stored. */
 int vmgb_spynet_level_input(const float* pyr, const float* flow_coarse, void* out8, int out8_dt, float* flow_up,
-                            int n_pairs, int B, int dir, int h, int w, void* stream);
+                            int n_pairs, int B, int dir, int h, int w, int semantics, void* stream);
 /* final: bilinear resize (align_corners=False) of flow [n,h_up,w_up,2] to [n,h,w,2] and rescale (vmg.py:113-121) */
 int vmgb_flow_resize(const float* flow, float* out, int n, int h_up, int w_up, int h, int w, void* stream);
 
@@ -215,6 +229,51 @@ int vmgb_pad_input(const float* x, float* out, int B, int T, int H, int W, int H
 int vmgb_mirror_check(const float* x, float* sumsq, int B, int T, long long frame_elems, void* stream);
 int vmgb_final_output(const void* y, int y_dt, int y_pitch, const float* x, float* out, int B, int T, int t0, int Tc,
                       int H, int W, void* stream);
+
+/* ==== the callers either side of the forward: frame I/O, Tester tiling / blending, metrics, ensemble ====
+ * Prototype grammar note: `double*` / `const double*` are fp64 device pointers unless stated otherwise. */
+
+/* ---- frame I/O (utils/eval_utils.py:8-36 read_image/read_seq_images; tools/Tester.py:217-222,249-250) ----------
+ * u8 -> f32: frames uint8 [T,H,W,3] -> fp32 [T,3,H,W] = u8 / 255 (numpy `astype(float32) / 255.`), bit-exact.
+ * f32 -> u8: clamp(0,1) -> * 255.0 -> round half to even -> uint8 [T,H,W,3] (Tester.evaluate), bit-exact.
+ * reverse_channels = 1 flips the channel order (cv2 BGR <-> RGB, eval_utils.py:19; cv2.imwrite(output[..., ::-1])). */
+int vmgb_frames_u8_to_f32(const void* frames_u8, float* out, int T, int H, int W, int reverse_channels, void* stream);
+int vmgb_frames_f32_to_u8(const float* frames, void* out_u8, int T, int H, int W, int reverse_channels, void* stream);
+
+/* ---- overlapped tile / window blending (tools/Tester.py:107-143 test_image, :146-177 test_clips) ----------------
+ * accumulate: E[b, t0+t, c, h0+y, w0+x] += patch[b,t,c,y,x] and count[t0+t, h0+y, w0+x] += 1 for the patch samples the
+ *             reference does not zero: frames [zt0, Tp-zt1), rows [zh0, ph-zh1), columns [zw0, pw-zw1).
+ *             patch fp32 [B,Tp,C,ph,pw]; E fp32 [B,Te,C,He,We]; count fp32 [Te,He,We] (may be NULL).
+ *             Units must be accumulated in the reference's loop order for bit-identical sums (stream order does that).
+ * normalize : E /= count (fp32 division, broadcast over batch and channels)   -- `E.div_(W)`
+ * finalize  : uint8 [T,H,W,3] = round(clamp(E / count, 0, 1) * 255) for B = 1, C = 3 (count may be NULL: no division) */
+int vmgb_blend_accumulate(const float* patch, float* E, float* count, int B, int Tp, int C, int ph, int pw, int Te, int He, int We,
+                          int t0, int h0, int w0, int zt0, int zt1, int zh0, int zh1, int zw0, int zw1, void* stream);
+int vmgb_blend_normalize(float* E, const float* count, int B, int Te, int C, int He, int We, void* stream);
+int vmgb_blend_finalize_u8(const float* E, const float* count, void* out_u8, int T, int H, int W, int reverse_channels, void* stream);
+
+/* ---- augmentation of the self-ensemble route (tools/Tester.py:387-445 augment / augment_inverse) ---------------
+ * per [H,W] plane: hflip (reverse W), then vflip (reverse H), then transpose (H <-> W); dst is [planes, W, H] when
+ * transpose is set.  augment_inverse applies the SAME sequence (the reference does; it is an involution for
+ * hflip == vflip or transpose == 0). */
+int vmgb_augment(const float* src, float* dst, long long planes, int H, int W, int hflip, int vflip, int transpose, void* stream);
+
+/* ---- metrics (utils/metrics.py:11-70; tools/test_reds4.py:194-218) ---------------------------------------------
+ * sse_u8 : *out_sum (64-bit integer, ZEROED by the caller) += sum (a-b)^2 over n uint8 samples; exact, so
+ *          calculate_psnr = 20 log10(255 / sqrt(sse / n)) is bit-reproducible on the host.
+ * sse_f32 / sse_f64: fp64 sum of squared differences (deterministic two-stage reduction; scratch from
+ *          vmgb_metrics_scratch_doubles); clamp01 clamps both fp32 inputs to [0,1] first (Tester.test_clips_max).
+ * rgb_to_y: float64 Y of skimage.color.rgb2ycbcr on uint8 RGB: 16 + 65.481 r + 128.553 g + 24.966 b, r,g,b = u8 * (1/255).
+ * ssim   : structural_similarity with the 11x11 Gaussian window (window11 = HOST pointer to the 11 weights of
+ *          cv2.getGaussianKernel(11, 1.5)), valid region, float64; dt 0 = n_img x uint8 [H,W,n_planes] (mean over the
+ *          planes, metrics.py:46-50), dt 1 = n_img x float64 [H,W] (n_planes = 1).  out_per_img: fp64 [n_img]. */
+int vmgb_sse_u8(const void* a, const void* b, long long n, long long* out_sum, void* stream);
+long long vmgb_metrics_scratch_doubles(int n_img, int H, int W, int n_planes);
+int vmgb_sse_f32(const float* a, const float* b, long long n, int clamp01, double* scratch, double* out_sum, void* stream);
+int vmgb_sse_f64(const double* a, const double* b, long long n, double* scratch, double* out_sum, void* stream);
+int vmgb_rgb_to_y(const void* rgb_u8, double* y, long long pixels, void* stream);
+int vmgb_ssim(const void* a, const void* b, int dt, int n_img, int H, int W, int n_planes, const double* window11, double* scratch,
+              double* out_per_img, void* stream);
 
 #ifdef __cplusplus
 }

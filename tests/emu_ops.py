@@ -12,9 +12,14 @@ import torch.nn.functional as F
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
 EPI_STORE, EPI_RESADD, EPI_GATE = 0, 1, 2
+COORD_ATEN_CPU, COORD_ATEN_CUDA = 0, 1      # ignored here: torch follows the device the tensors live on
 
 
 def require_device():
+    pass
+
+
+def check_same_device(x, param):
     pass
 
 
@@ -189,14 +194,14 @@ def groupnorm1_relu(x, gamma, beta, eps=1e-5):
 
 def _warp(x_nchw, flow_nhw2, mode):
     n, c, h, w = x_nchw.shape
-    gy, gx = torch.meshgrid(torch.arange(0, h), torch.arange(0, w), indexing='ij')
+    gy, gx = torch.meshgrid(torch.arange(0, h, device=x_nchw.device), torch.arange(0, w, device=x_nchw.device), indexing='ij')
     g = torch.stack((gx, gy), 2).float() + flow_nhw2
     gxn = 2.0 * g[..., 0] / max(w - 1, 1) - 1.0
     gyn = 2.0 * g[..., 1] / max(h - 1, 1) - 1.0
     return F.grid_sample(x_nchw, torch.stack((gxn, gyn), 3), mode=mode, padding_mode='border', align_corners=True)
 
 
-def flow_warp_bilinear(x, flow, out=None):
+def flow_warp_bilinear(x, flow, out=None, semantics=0):
     v = _warp(x.float().permute(0, 3, 1, 2), flow, 'bilinear').permute(0, 2, 3, 1).to(x.dtype)
     if out is not None:
         out.copy_(v)
@@ -204,15 +209,20 @@ def flow_warp_bilinear(x, flow, out=None):
     return v.contiguous()
 
 
-def flow_warp_nearest(loc, flow, K2, out):
+def flow_warp_nearest(loc, flow, K2, out, semantics=0):
     v = _warp(loc[..., :K2].permute(0, 3, 1, 2), flow, 'nearest').permute(0, 2, 3, 1)
     out[..., :K2] = v
     return out
 
 
+def flow_warp_fused(x, flow, loc, K2, loc_out, out=None, semantics=0):
+    flow_warp_nearest(loc, flow, K2, loc_out)
+    return flow_warp_bilinear(x, flow, out=out)
+
+
 def loc_identity_(loc, c0):
     n, h, w, _ = loc.shape
-    gy, gx = torch.meshgrid(torch.arange(0, h), torch.arange(0, w), indexing='ij')
+    gy, gx = torch.meshgrid(torch.arange(0, h, device=loc.device), torch.arange(0, w, device=loc.device), indexing='ij')
     loc[..., c0] = gx.float()
     loc[..., c0 + 1] = gy.float()
     return loc
@@ -268,7 +278,7 @@ def avgpool2(x):
     return F.avg_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).contiguous()
 
 
-def spynet_level_input(pyr, flow_coarse, n_pairs, B, direction, out_dtype=torch.float32):
+def spynet_level_input(pyr, flow_coarse, n_pairs, B, direction, out_dtype=torch.float32, semantics=0):
     _, h, w, _ = pyr.shape
     ref = pyr[B:B + n_pairs] if direction == 0 else pyr[:n_pairs]
     sup = pyr[:n_pairs] if direction == 0 else pyr[B:B + n_pairs]
@@ -308,3 +318,52 @@ def final_output(y, x, out, t0):
     up = up.view(B, Tc, 3, 4 * H, 4 * W)
     out[:, t0:t0 + Tc] = y.float().view(Tc, B, 4 * H, 4 * W, 3).permute(1, 0, 4, 2, 3) + up
     return out
+
+
+# ---- callers either side of the forward (vmg_b200/tester.py host logic on CPU) -----------------------------------
+def frames_u8_to_f32(frames_u8, reverse_channels=False):
+    x = frames_u8.flip(-1) if reverse_channels else frames_u8
+    return (x.float() / 255.0).permute(0, 3, 1, 2).contiguous().unsqueeze(0)
+
+
+def frames_f32_to_u8(frames, reverse_channels=False, out=None):
+    if frames.dim() == 5:
+        frames = frames[0]
+    v = torch.round(frames.clamp(0, 1) * 255.0).to(torch.uint8).permute(0, 2, 3, 1)
+    return (v.flip(-1) if reverse_channels else v).contiguous()
+
+
+def blend_accumulate_(E, count, patch, t0, h0, w0, zero_t=(0, 0), zero_h=(0, 0), zero_w=(0, 0)):
+    B, Tp, C, ph, pw = patch.shape
+    m = torch.zeros((Tp, ph, pw))
+    m[zero_t[0]:Tp - zero_t[1], zero_h[0]:ph - zero_h[1], zero_w[0]:pw - zero_w[1]] = 1.0
+    E[:, t0:t0 + Tp, :, h0:h0 + ph, w0:w0 + pw] += patch * m[None, :, None]
+    if count is not None:
+        count[t0:t0 + Tp, h0:h0 + ph, w0:w0 + pw] += m
+    return E
+
+
+def blend_normalize_(E, count):
+    E.div_(count[None, :, None])
+    return E
+
+
+def augment(x, hflip, vflip, transpose):
+    if hflip:
+        x = x.flip(-1)
+    if vflip:
+        x = x.flip(-2)
+    if transpose:
+        x = x.transpose(-1, -2)
+    return x.contiguous()
+
+
+def sse_f32(a, b, clamp01=False):
+    if clamp01:
+        a, b = a.clamp(0, 1), b.clamp(0, 1)
+    return ((a.double() - b.double()) ** 2).sum().reshape(1)
+
+
+def blend_finalize_u8(E, count=None, reverse_channels=False):
+    v = E if count is None else E / count[None, :, None]
+    return frames_f32_to_u8(v, reverse_channels)

@@ -4,6 +4,7 @@
 namespace vmgb {
 int g_last_cuda_error = 0;
 long long g_launch_count = 0;
+int g_pack_pending = 0;
 }  // namespace vmgb
 
 extern "C" int vmgb_version(void) { return 100; }

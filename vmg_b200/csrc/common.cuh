@@ -9,6 +9,7 @@ namespace vmgb {
 
 extern int g_last_cuda_error;
 extern long long g_launch_count;
+extern int g_pack_pending;      // a tcgen05 weight pack was launched since the last programmatic-dependent-launch kernel
 
 inline int check_launch() {
   ++g_launch_count;
@@ -75,10 +76,15 @@ __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
 //   g = 2*(x+flow)/(size-1) - 1          (trajectory.py:101-106)
 //   u = ((g+1)/2)*(size-1)               (ATen GridSampler.cuh grid_sampler_unnormalize)
 //   u = min(size-1, max(u, 0))           (clip_coordinates)
-__device__ __forceinline__ float warp_coord(float base, float flow, int size) {
+// `sem` selects whose rounding the division by the Python scalar (size-1) follows:
+//   VMGB_COORD_ATEN_CPU  : true division (ATen CPU div kernel)
+//   VMGB_COORD_ATEN_CUDA : multiplication by the fp32 reciprocal (ATen CUDA div kernel with a CPU-scalar divisor computes
+//                          a * (1/b), "may lose one bit of precision") -- what the reference's own GPU forward does
+__device__ __forceinline__ float warp_coord(float base, float flow, int size, int sem) {
   float denom = (float)max(size - 1, 1);
   float gf = __fadd_rn(base, flow);
-  float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, gf), denom), 1.0f);
+  float q = sem == VMGB_COORD_ATEN_CUDA ? __fmul_rn(__fmul_rn(2.0f, gf), __fdiv_rn(1.0f, denom)) : __fdiv_rn(__fmul_rn(2.0f, gf), denom);
+  float g = __fsub_rn(q, 1.0f);
   float u = __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), (float)(size - 1));
   return fminf((float)(size - 1), fmaxf(u, 0.f));
 }

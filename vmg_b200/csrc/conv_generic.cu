@@ -346,5 +346,6 @@ extern "C" int vmgb_pack_weight_tc(const void* w_oihw, void* w_packed_bf16, int 
   long long total = (long long)Cout * Kp * R * S;
   int blocks = (int)((total + 255) / 256); if (blocks > 4096) blocks = 4096;
   pack_weight_tc_kernel<<<blocks, 256, 0, as_stream(stream)>>>((const float*)w_oihw, (__nv_bfloat16*)w_packed_bf16, Cout, Cin_g, Kp, R * S, groups);
+  g_pack_pending = 1;      // the next programmatic-dependent-launch conv must wait for this kernel before it loads weights
   return check_launch();
 }

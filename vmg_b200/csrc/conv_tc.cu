@@ -1398,6 +1398,7 @@ static int g_res_tma = 1;     // VMGB_RES_TMA=0: residual of the pair kernel by 
 static int g_ws2_multi = 1;   // VMGB_WS2_MULTI=0: multi-source convs stay on the per-tap kernel (A/B switch)
 static int g_wst_gate = 1;    // VMGB_WST_GATE=0: gate epilogue on the per-thread staging path (A/B switch)
 static int g_no_wst = 0;      // VMGB_NO_WST=1: A/B switch (tools/microbench.py) for the warp-private staging epilogue
+static int g_device = -1;     // the device tc_init ran on: attributes / SM count are per device, other devices are refused
 
 static void tc_init() {
   void* fn = nullptr;
@@ -1412,6 +1413,7 @@ static void tc_init() {
   if (const char* e = getenv("VMGB_WST_GATE")) g_wst_gate = atoi(e);      // A/B switch for tools/microbench.py
   int dev = 0;
   cudaGetDevice(&dev);
+  g_device = dev;
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (g_smem_optin > 0) {
@@ -1471,6 +1473,10 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   if (Kp < Cin_g) return VMGB_EINVAL;
   std::call_once(g_once, tc_init);
   if (!g_encode || g_num_sms <= 0) return VMGB_EUNSUPPORTED;
+  {   // one process drives one GPU (torchrun): the opt-in shared-memory attributes and the SM count were set for g_device only
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != g_device) return VMGB_EUNSUPPORTED;
+  }
 
   TcP p;
   p.n_img = n_img; p.H = H; p.W = W; p.Cin_g = Cin_g; p.Cout_g = Cout_g; p.groups = groups; p.R = R; p.S = S; p.n_src = n_src;
@@ -1571,7 +1577,10 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       cudaLaunchAttribute at[2];
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
+      // the kernel loads its weight slice BEFORE griddepcontrol.wait (weights are static); a launch that directly follows a
+      // weight (re)pack on this stream must therefore not overlap its predecessor
+      cfg.attrs = at; cfg.numAttrs = (g_pdl && !g_pack_pending) ? 2 : 1;
+      g_pack_pending = 0;
       cudaError_t e = R == 3 ? cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel<3>, mA[0], mA[1], mA[2], mB, mR, p)
                              : cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel<7>, mA[0], mA[1], mA[2], mB, mR, p);
       if (e != cudaSuccess) { g_last_cuda_error = (int)e; return VMGB_ECUDA; }

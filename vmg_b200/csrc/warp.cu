@@ -27,13 +27,13 @@ __device__ __forceinline__ float scale_of(int in_size, int out_size, bool align)
 // feature warp: bilinear, border, align_corners=True.  One thread per (pixel, 4 channels).
 // ---------------------------------------------------------------------------------------------
 __global__ void flow_warp_bilinear_kernel(const void* x, int x_dt, int x_pitch, const float* __restrict__ flow, void* out, int out_dt,
-                                          int out_pitch, int n, int h, int w, int C, long long total) {
+                                          int out_pitch, int n, int h, int w, int C, int sem, long long total) {
   const int C4 = C >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4); const long long pix = i / C4;
     const int px = (int)(pix % w); const long long t = pix / w; const int py = (int)(t % h); const int img = (int)(t / h);
     const float2 f = *reinterpret_cast<const float2*>(flow + pix * 2);
-    const float ix = warp_coord((float)px, f.x, w), iy = warp_coord((float)py, f.y, h);
+    const float ix = warp_coord((float)px, f.x, w, sem), iy = warp_coord((float)py, f.y, h, sem);
     const float fx0 = floorf(ix), fy0 = floorf(iy);
     const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
     const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix, wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
@@ -54,13 +54,13 @@ __global__ void flow_warp_bilinear_kernel(const void* x, int x_dt, int x_pitch, 
 // generic kernel above, so the results are bit-identical); half the threads and half the redundant coordinate work
 __global__ void __launch_bounds__(256) flow_warp_bilinear8_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch, const float* __restrict__ flow,
                                                                  __nv_bfloat16* __restrict__ out, int out_pitch, int n, int h, int w, int C,
-                                                                 long long total) {
+                                                                 int sem, long long total) {
   const int C8 = C >> 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % C8); const long long pix = i / C8;
     const int px = (int)(pix % w); const long long t = pix / w; const int py = (int)(t % h); const int img = (int)(t / h);
     const float2 f = *reinterpret_cast<const float2*>(flow + pix * 2);
-    const float ix = warp_coord((float)px, f.x, w), iy = warp_coord((float)py, f.y, h);
+    const float ix = warp_coord((float)px, f.x, w, sem), iy = warp_coord((float)py, f.y, h, sem);
     const float fx0 = floorf(ix), fy0 = floorf(iy);
     const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
     const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix, wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
@@ -100,12 +100,12 @@ __global__ void __launch_bounds__(256) flow_warp_bilinear8_kernel(const __nv_bfl
 
 // location warp: nearest, border (locations stay exact in-range integers)
 __global__ void flow_warp_nearest_kernel(const float* __restrict__ loc, int in_pitch, const float* __restrict__ flow,
-                                         float* __restrict__ out, int out_pitch, int n, int h, int w, int K2, long long total) {
+                                         float* __restrict__ out, int out_pitch, int n, int h, int w, int K2, int sem, long long total) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % K2); const long long pix = i / K2;
     const int px = (int)(pix % w); const long long t = pix / w; const int py = (int)(t % h); const int img = (int)(t / h);
     const float2 f = *reinterpret_cast<const float2*>(flow + pix * 2);
-    const int sx = (int)rintf(warp_coord((float)px, f.x, w)), sy = (int)rintf(warp_coord((float)py, f.y, h));
+    const int sx = (int)rintf(warp_coord((float)px, f.x, w, sem)), sy = (int)rintf(warp_coord((float)py, f.y, h, sem));
     out[pix * out_pitch + c] = loc[(((long long)img * h + sy) * w + sx) * in_pitch + c];
   }
 }
@@ -113,14 +113,74 @@ __global__ void flow_warp_nearest_kernel(const float* __restrict__ loc, int in_p
 // one thread per (pixel, tracked location = 2 floats): half the threads and coordinate work of the scalar kernel
 __global__ void __launch_bounds__(256) flow_warp_nearest2_kernel(const float* __restrict__ loc, int in_pitch, const float* __restrict__ flow,
                                                                 float* __restrict__ out, int out_pitch, int n, int h, int w, int K,
-                                                                long long total) {
+                                                                int sem, long long total) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % K); const long long pix = i / K;
     const int px = (int)(pix % w); const long long t = pix / w; const int py = (int)(t % h); const int img = (int)(t / h);
     const float2 f = *reinterpret_cast<const float2*>(flow + pix * 2);
-    const int sx = (int)rintf(warp_coord((float)px, f.x, w)), sy = (int)rintf(warp_coord((float)py, f.y, h));
+    const int sx = (int)rintf(warp_coord((float)px, f.x, w, sem)), sy = (int)rintf(warp_coord((float)py, f.y, h, sem));
     *reinterpret_cast<float2*>(out + pix * out_pitch + 2 * k) =
         *reinterpret_cast<const float2*>(loc + (((long long)img * h + sy) * w + sx) * in_pitch + 2 * k);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// flow_warp_fused: ONE launch per trajectory step for both warps that share a flow field (trajectory.py:330-333):
+// the bilinear feature warp (bf16, 8 channels per work item) and the nearest warp of all K tracked locations
+// (one (x, y) pair per work item).  Work item i of pixel p: i < C/8 -> feature group i, else location i - C/8.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) flow_warp_fused_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch, const float* __restrict__ flow,
+                                                             __nv_bfloat16* __restrict__ out, int out_pitch, const float* __restrict__ loc,
+                                                             int loc_in_pitch, float* __restrict__ loc_out, int loc_out_pitch, int K, int n, int h,
+                                                             int w, int C, int sem, long long total) {
+  const int C8 = C >> 3, per = C8 + K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int item = (int)(i % per); const long long pix = i / per;
+    const int px = (int)(pix % w); const long long t = pix / w; const int py = (int)(t % h); const int img = (int)(t / h);
+    const float2 f = *reinterpret_cast<const float2*>(flow + pix * 2);
+    const float ix = warp_coord((float)px, f.x, w, sem), iy = warp_coord((float)py, f.y, h, sem);
+    const long long ib = (long long)img * h;
+    if (item >= C8) {
+      const int k = item - C8;
+      const int sx = (int)rintf(ix), sy = (int)rintf(iy);
+      *reinterpret_cast<float2*>(loc_out + pix * loc_out_pitch + 2 * k) =
+          *reinterpret_cast<const float2*>(loc + ((ib + sy) * w + sx) * loc_in_pitch + 2 * k);
+      continue;
+    }
+    const int c8 = item;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+    const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix, wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const int ys[4] = {y0, y0, y1, y1}, xs[4] = {x0, x1, x0, x1};
+    const float ws[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
+    uint4 v[4];
+    bool ok[4];
+#pragma unroll
+    for (int tp = 0; tp < 4; ++tp) {
+      ok[tp] = ys[tp] >= 0 && ys[tp] < h && xs[tp] >= 0 && xs[tp] < w;
+      v[tp] = ok[tp] ? __ldg(reinterpret_cast<const uint4*>(x + ((ib + ys[tp]) * w + xs[tp]) * x_pitch + c8 * 8)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int tp = 0; tp < 4; ++tp) {
+      if (ok[tp]) {
+        const uint32_t wd[4] = {v[tp].x, v[tp].y, v[tp].z, v[tp].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc[2 * q] += __uint_as_float(wd[q] << 16) * ws[tp];
+          acc[2 * q + 1] += __uint_as_float(wd[q] & 0xffff0000u) * ws[tp];
+        }
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+      o[q] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(out + pix * out_pitch + c8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -185,7 +245,7 @@ __global__ void avgpool2_kernel(const float* __restrict__ x, float* __restrict__
 
 // one thread per output pixel of one (ref, supp) pair
 __global__ void spynet_level_input_kernel(const float* __restrict__ pyr, const float* __restrict__ fc, void* out8, int out8_dt,
-                                          float* __restrict__ fup, int B, int dir, int h, int w, long long total) {
+                                          float* __restrict__ fup, int B, int dir, int h, int w, int sem, long long total) {
   const int hc = h / 2, wc = w / 2;
   const float sch = scale_of(hc, h, true), scw = scale_of(wc, w, true);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -204,7 +264,7 @@ __global__ void spynet_level_input_kernel(const float* __restrict__ pyr, const f
       fx = (ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x)) * 2.0f;
       fy = (ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y)) * 2.0f;
     }
-    const float ix = warp_coord((float)px, fx, w), iy = warp_coord((float)py, fy, h);
+    const float ix = warp_coord((float)px, fx, w, sem), iy = warp_coord((float)py, fy, h, sem);
     const float fx0 = floorf(ix), fy0 = floorf(iy);
     const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
     const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix, wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
@@ -294,31 +354,46 @@ __global__ void final_output_kernel(const void* y, int y_dt, int y_pitch, const 
 
 using namespace vmgb;
 
+static bool sem_ok(int sem) { return sem == VMGB_COORD_ATEN_CPU || sem == VMGB_COORD_ATEN_CUDA; }
+
 extern "C" int vmgb_flow_warp_bilinear(const void* x, int x_dt, int x_pitch, const float* flow, void* out, int out_dt, int out_pitch,
-                                       int n, int h, int w, int C, void* stream) {
-  if (!x || !flow || !out || !dt_ok(x_dt) || !dt_ok(out_dt) || (C & 3) || (x_pitch & 3) || (out_pitch & 3)) return VMGB_EINVAL;
+                                       int n, int h, int w, int C, int semantics, void* stream) {
+  if (!x || !flow || !out || !dt_ok(x_dt) || !dt_ok(out_dt) || (C & 3) || (x_pitch & 3) || (out_pitch & 3) || !sem_ok(semantics)) return VMGB_EINVAL;
   if (x_dt == VMGB_BF16 && out_dt == VMGB_BF16 && (C & 7) == 0 && (x_pitch & 7) == 0 && (out_pitch & 7) == 0 &&
       !(((uintptr_t)x | (uintptr_t)out) & 15)) {
     const long long total8 = (long long)n * h * w * (C / 8);
     flow_warp_bilinear8_kernel<<<grid_for2(total8, 256, 148 * 32), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, x_pitch, flow,
-                                                                                                 (__nv_bfloat16*)out, out_pitch, n, h, w, C, total8);
+                                                                                                 (__nv_bfloat16*)out, out_pitch, n, h, w, C, semantics, total8);
     return check_launch();
   }
   long long total = (long long)n * h * w * (C / 4);
-  flow_warp_bilinear_kernel<<<grid_for2(total, 256, 148 * 32), 256, 0, as_stream(stream)>>>(x, x_dt, x_pitch, flow, out, out_dt, out_pitch, n, h, w, C, total);
+  flow_warp_bilinear_kernel<<<grid_for2(total, 256, 148 * 32), 256, 0, as_stream(stream)>>>(x, x_dt, x_pitch, flow, out, out_dt, out_pitch, n, h, w, C, semantics, total);
   return check_launch();
 }
 
 extern "C" int vmgb_flow_warp_nearest(const float* loc, int in_pitch, const float* flow, float* out, int out_pitch, int n, int h,
-                                      int w, int K2, void* stream) {
-  if (!loc || !flow || !out || K2 <= 0 || loc == out) return VMGB_EINVAL;
+                                      int w, int K2, int semantics, void* stream) {
+  if (!loc || !flow || !out || K2 <= 0 || loc == out || !sem_ok(semantics)) return VMGB_EINVAL;
   if (!(K2 & 1) && !(in_pitch & 1) && !(out_pitch & 1) && !(((uintptr_t)loc | (uintptr_t)out) & 7)) {
     const long long total2 = (long long)n * h * w * (K2 / 2);
-    flow_warp_nearest2_kernel<<<grid_for2(total2, 256, 148 * 32), 256, 0, as_stream(stream)>>>(loc, in_pitch, flow, out, out_pitch, n, h, w, K2 / 2, total2);
+    flow_warp_nearest2_kernel<<<grid_for2(total2, 256, 148 * 32), 256, 0, as_stream(stream)>>>(loc, in_pitch, flow, out, out_pitch, n, h, w, K2 / 2, semantics, total2);
     return check_launch();
   }
   long long total = (long long)n * h * w * K2;
-  flow_warp_nearest_kernel<<<grid_for2(total, 256, 148 * 32), 256, 0, as_stream(stream)>>>(loc, in_pitch, flow, out, out_pitch, n, h, w, K2, total);
+  flow_warp_nearest_kernel<<<grid_for2(total, 256, 148 * 32), 256, 0, as_stream(stream)>>>(loc, in_pitch, flow, out, out_pitch, n, h, w, K2, semantics, total);
+  return check_launch();
+}
+
+extern "C" int vmgb_flow_warp_fused(const void* x, int x_pitch, const float* flow, void* out, int out_pitch, const float* loc, int loc_in_pitch,
+                                    float* loc_out, int loc_out_pitch, int K2, int n, int h, int w, int C, int semantics, void* stream) {
+  if (!x || !flow || !out || !loc || !loc_out || loc == loc_out || K2 <= 0 || (K2 & 1) || !sem_ok(semantics)) return VMGB_EINVAL;
+  if ((C & 7) || (x_pitch & 7) || (out_pitch & 7) || (((uintptr_t)x | (uintptr_t)out) & 15) || (loc_in_pitch & 1) || (loc_out_pitch & 1) ||
+      (((uintptr_t)loc | (uintptr_t)loc_out) & 7))
+    return VMGB_EUNSUPPORTED;      // the caller falls back to the two separate launches
+  const long long total = (long long)n * h * w * (C / 8 + K2 / 2);
+  flow_warp_fused_kernel<<<grid_for2(total, 256, 148 * 32), 256, 0, as_stream(stream)>>>(
+      (const __nv_bfloat16*)x, x_pitch, flow, (__nv_bfloat16*)out, out_pitch, loc, loc_in_pitch, loc_out, loc_out_pitch, K2 / 2, n, h, w, C,
+      semantics, total);
   return check_launch();
 }
 
@@ -355,10 +430,10 @@ extern "C" int vmgb_avgpool2(const float* x, float* out, int n, int H, int W, in
 }
 
 extern "C" int vmgb_spynet_level_input(const float* pyr, const float* flow_coarse, void* out8, int out8_dt, float* flow_up, int n_pairs, int B,
-                                       int dir, int h, int w, void* stream) {
-  if (!pyr || !out8 || !flow_up || !dt_ok(out8_dt) || n_pairs < 1 || B < 1 || (flow_coarse && ((h & 1) || (w & 1)))) return VMGB_EINVAL;
+                                       int dir, int h, int w, int semantics, void* stream) {
+  if (!pyr || !out8 || !flow_up || !dt_ok(out8_dt) || n_pairs < 1 || B < 1 || (flow_coarse && ((h & 1) || (w & 1))) || !sem_ok(semantics)) return VMGB_EINVAL;
   long long total = (long long)n_pairs * h * w;
-  spynet_level_input_kernel<<<grid_for2(total), 256, 0, as_stream(stream)>>>(pyr, flow_coarse, out8, out8_dt, flow_up, B, dir, h, w, total);
+  spynet_level_input_kernel<<<grid_for2(total), 256, 0, as_stream(stream)>>>(pyr, flow_coarse, out8, out8_dt, flow_up, B, dir, h, w, semantics, total);
   return check_launch();
 }
 

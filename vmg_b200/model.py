@@ -229,6 +229,11 @@ class VMG(nn.Module):
         refuse(not ltam or not traj_scale or traj_refine is not None, 'ltam=False / traj_scale=False / traj_refine')
         refuse(channel_mixer not in ('vanilla', 'rcab'), f'channel_mixer={channel_mixer!r}')
         refuse(temporal_type[0] is not False, 'a first stage without trajectory alignment')
+        # shapes the kernels take (csrc/ltam.cu: 4 heads, C/heads/4 in {4,7,8,9}; multi-source convs: C % 16 == 0)
+        refuse(traj_heads[0] != 4, 'traj_heads[0] != 4')
+        refuse(embed_dim[0] % 16 != 0 or embed_dim[0] // 16 not in (4, 7, 8, 9), 'embed_dim[0] outside {64, 112, 128, 144}')
+        refuse(embed_dim[-1] != embed_dim[0], 'embed_dim[-1] != embed_dim[0]')
+        refuse(any(d % 8 for d in embed_dim), 'embed_dim not a multiple of 8')
         self.flow_smooth, self.region = flow_smooth, smooth_region_range
         self.r_scaling, self.m_scaling = float(r_scaling), float(m_scaling)
         self.n_groups, self.twins = n_groups, list(twins)
@@ -281,6 +286,9 @@ class VMG(nn.Module):
         self._graphs, self._graph_stamp = {}, None
         self.use_cuda_graph = os.environ.get('VMGB_NO_GRAPH', '0') != '1'
         self.recon_chunk = 8     # frames per reconstruction-head chunk (bounds the 4x-resolution temporaries)
+        # rounding of the flow_warp coordinate normalisation (include/vmgb.h VMGB_COORD_*): 'cuda' = what the reference's
+        # own forward computes on a GPU (ATen CUDA divides by a Python scalar as a * (1/b)), 'cpu' = ATen CPU (true division)
+        self.coord_semantics = 'cuda'
 
     @staticmethod
     def _init_weights(m):               # vmg.py:415-424
@@ -298,6 +306,12 @@ class VMG(nn.Module):
     @property
     def _adt(self):
         return torch.bfloat16 if self.precision == 'bf16' else torch.float32
+
+    @property
+    def _sem(self):
+        if self.coord_semantics not in ('cuda', 'cpu'):
+            raise ValueError("coord_semantics must be 'cuda' or 'cpu'")
+        return _ops.COORD_ATEN_CUDA if self.coord_semantics == 'cuda' else _ops.COORD_ATEN_CPU
 
     def _pc(self, mod, groups=1, tc=None, force=False):
         """Packed kernel-side weights of a Conv2d/Linear holder, re-packed when the parameter changed."""
@@ -332,7 +346,7 @@ class VMG(nn.Module):
         for direction in ((0,) if mirror else (0, 1)):
             flow = None
             for level in range(6):
-                y, fup = o.spynet_level_input(pyr[level], flow, n_pairs, B, direction, out_dtype=self._adt)
+                y, fup = o.spynet_level_input(pyr[level], flow, n_pairs, B, direction, out_dtype=self._adt, semantics=self._sem)
                 convs = self.spynet.basic_module[level].basic_module
                 for m in range(4):
                     y = o.conv2d(y, self._pc(convs[m].conv, tc=tc), act=o.ACT_RELU, use_tc=tc)
@@ -438,8 +452,7 @@ class VMG(nn.Module):
                 feat_in = torch.zeros((2 * n, H, W, C), device=x.device, dtype=x.dtype)
             else:
                 flow = fl[j - 1]
-                warped = o.flow_warp_bilinear(prev, flow)
-                o.flow_warp_nearest(loc[cur_loc], flow, 2 * K, loc[1 - cur_loc])
+                warped = o.flow_warp_fused(prev, flow, loc[cur_loc], 2 * K, loc[1 - cur_loc], semantics=self._sem)
                 cur_loc = 1 - cur_loc
                 att = o.ltam_wins(qp[j], qp[0], fbuf[0], stride * step_elems, K, loc[cur_loc], rel, decay, st.heads)
                 feat_in = o.linear(att, proj, epi=o.EPI_RESADD, res=warped)
@@ -488,6 +501,7 @@ class VMG(nn.Module):
         o.require_device()
         if self.training:
             raise NotImplementedError('vmg_b200.VMG implements the inference forward only; call .eval()')
+        o.check_same_device(x, self.input_proj.proj[0].weight)
         B, T, Cin, H, W = x.shape
         assert H >= 64 and W >= 64, 'The height and width must larger than 64.'
         if T != self.num_out_frames:
@@ -500,7 +514,7 @@ class VMG(nn.Module):
         if stamp != self._graph_stamp:
             self._graphs.clear()
             self._graph_stamp = stamp
-        key = (tuple(x.shape), self.frames_mirror, self.precision, x.device.index)
+        key = (tuple(x.shape), self.frames_mirror, self.precision, x.device.index, self.coord_semantics)
         ent = self._graphs.get(key)
         if ent is None:                       # first call: eager (also packs the weights)
             self._graphs[key] = 'warm'

@@ -20,11 +20,12 @@ LIB_PATH = os.environ.get('VMGB_LIB') or os.path.join(_HERE, 'libvmgb.so')      
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
 EPI_STORE, EPI_RESADD, EPI_GATE = 0, 1, 2
+COORD_ATEN_CPU, COORD_ATEN_CUDA = 0, 1      # see include/vmgb.h
 
 _CTYPES = {
     'int': ctypes.c_int, 'float': ctypes.c_float, 'long long': ctypes.c_longlong,
     'void*': ctypes.c_void_p, 'const void*': ctypes.c_void_p, 'float*': ctypes.c_void_p,
-    'const float*': ctypes.c_void_p, 'long long*': ctypes.c_void_p, 'const long long*': ctypes.c_void_p, 'const char*': ctypes.c_char_p, 'void': None,
+    'const float*': ctypes.c_void_p, 'double*': ctypes.c_void_p, 'const double*': ctypes.c_void_p, 'long long*': ctypes.c_void_p, 'const long long*': ctypes.c_void_p, 'const char*': ctypes.c_char_p, 'void': None,
 }
 
 
@@ -63,19 +64,31 @@ def lib():
     return _lib
 
 
-_checked = False
+_checked = None      # ordinal of the device the library was first used on (one process drives one GPU)
 
 
 def require_device():
     global _checked
-    if _checked:
-        return
     if not torch.cuda.is_available():
         raise RuntimeError('vmg_b200 needs a CUDA device (sm_100a); there is no CPU fallback.')
+    cur = torch.cuda.current_device()
+    if _checked is not None:
+        if cur != _checked:
+            raise RuntimeError(f'vmg_b200 was initialised on cuda:{_checked} and now runs on cuda:{cur}: one process drives '
+                               'one GPU (launch one process per GPU with torchrun)')
+        return
     rc = lib().vmgb_device_check()
     if rc != 0:
         raise RuntimeError(f'vmg_b200 kernels are sm_100a-only; vmgb_device_check() = {rc}')
-    _checked = True
+    _checked = cur
+
+
+def check_same_device(x, param):
+    """Input, parameters and the current CUDA device must be the same GPU: the kernels take raw pointers and launch
+    on the current device's stream (a CPU tensor would become an illegal-address fault)."""
+    if not x.is_cuda or x.device != param.device or x.device.index != torch.cuda.current_device():
+        raise RuntimeError(f'vmg_b200.VMG: input on {x.device}, parameters on {param.device}, current device '
+                           f'cuda:{torch.cuda.current_device()} -- all three must be the same sm_100 GPU (there is no CPU path)')
 
 
 def _ck(rc, name):
@@ -393,7 +406,7 @@ def groupnorm1_relu(x, gamma, beta, eps=1e-5):
 # ---------------------------------------------------------------------------------------------
 # warps / trajectory
 # ---------------------------------------------------------------------------------------------
-def flow_warp_bilinear(x, flow, out=None):
+def flow_warp_bilinear(x, flow, out=None, semantics=COORD_ATEN_CUDA):
     require_device()
     n, h, w, C = x.shape
     xp, xpitch = _pix(x)
@@ -401,17 +414,41 @@ def flow_warp_bilinear(x, flow, out=None):
         out = torch.empty((n, h, w, C), device=x.device, dtype=x.dtype)
     op, opitch = _pix(out)
     assert flow.dtype == torch.float32 and flow.is_contiguous() and flow.shape == (n, h, w, 2)
-    _ck(lib().vmgb_flow_warp_bilinear(xp, _dt(x), xpitch, flow.data_ptr(), op, _dt(out), opitch, n, h, w, C, _stream()),
+    _ck(lib().vmgb_flow_warp_bilinear(xp, _dt(x), xpitch, flow.data_ptr(), op, _dt(out), opitch, n, h, w, C, semantics, _stream()),
         'vmgb_flow_warp_bilinear')
     return out
 
 
-def flow_warp_nearest(loc, flow, K2, out):
+def flow_warp_nearest(loc, flow, K2, out, semantics=COORD_ATEN_CUDA):
     require_device()
     n, h, w, pitch = loc.shape
     assert loc.is_contiguous() and out.is_contiguous() and out.shape == loc.shape and loc.dtype == torch.float32
     _ck(lib().vmgb_flow_warp_nearest(loc.data_ptr(), pitch, flow.data_ptr(), out.data_ptr(), pitch, n, h, w, K2,
-                                     _stream()), 'vmgb_flow_warp_nearest')
+                                     semantics, _stream()), 'vmgb_flow_warp_nearest')
+    return out
+
+
+def flow_warp_fused(x, flow, loc, K2, loc_out, out=None, semantics=COORD_ATEN_CUDA):
+    """Both warps of one trajectory step in one launch: returns the bilinear-warped features; the nearest-warped
+    first K2 location channels land in `loc_out`.  Shapes the fused kernel does not take (fp32 features, odd
+    pitches) go through the two separate launches."""
+    require_device()
+    n, h, w, C = x.shape
+    assert flow.dtype == torch.float32 and flow.is_contiguous() and flow.shape == (n, h, w, 2)
+    assert loc.is_contiguous() and loc_out.is_contiguous() and loc_out.shape == loc.shape and loc.dtype == torch.float32
+    if out is None:
+        out = torch.empty((n, h, w, C), device=x.device, dtype=x.dtype)
+    if x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16:
+        xp, xpitch = _pix(x)
+        op, opitch = _pix(out)
+        rc = lib().vmgb_flow_warp_fused(xp, xpitch, flow.data_ptr(), op, opitch, loc.data_ptr(), loc.shape[-1], loc_out.data_ptr(),
+                                        loc_out.shape[-1], K2, n, h, w, C, semantics, _stream())
+        if rc == 0:
+            return out
+        if rc != -2:
+            _ck(rc, 'vmgb_flow_warp_fused')
+    flow_warp_bilinear(x, flow, out=out, semantics=semantics)
+    flow_warp_nearest(loc, flow, K2, loc_out, semantics=semantics)
     return out
 
 
@@ -462,13 +499,13 @@ def avgpool2(x):
     return out
 
 
-def spynet_level_input(pyr, flow_coarse, n_pairs, B, direction, out_dtype=torch.float32):
+def spynet_level_input(pyr, flow_coarse, n_pairs, B, direction, out_dtype=torch.float32, semantics=COORD_ATEN_CUDA):
     require_device()
     _, h, w, _ = pyr.shape
     out8 = torch.empty((n_pairs, h, w, 8), device=pyr.device, dtype=out_dtype)
     fup = torch.empty((n_pairs, h, w, 2), device=pyr.device, dtype=torch.float32)
     _ck(lib().vmgb_spynet_level_input(pyr.data_ptr(), _ptr(flow_coarse), out8.data_ptr(), _dt(out8), fup.data_ptr(), n_pairs, B,
-                                      direction, h, w, _stream()), 'vmgb_spynet_level_input')
+                                      direction, h, w, semantics, _stream()), 'vmgb_spynet_level_input')
     return out8, fup
 
 
@@ -508,4 +545,132 @@ def final_output(y, x, out, t0):
     yp, ypitch = _pix(y)
     _ck(lib().vmgb_final_output(yp, _dt(y), ypitch, x.data_ptr(), out.data_ptr(), B, T, t0, Tc, H, W, _stream()),
         'vmgb_final_output')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# callers either side of the forward: frame I/O, blending, augmentation, metrics
+# ---------------------------------------------------------------------------------------------
+def frames_u8_to_f32(frames_u8, reverse_channels=False):
+    """uint8 [T,H,W,3] (device) -> fp32 [1,T,3,H,W] in [0,1] (Tester.evaluate: astype(float32)/255, permute, unsqueeze)."""
+    require_device()
+    assert frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous() and frames_u8.dim() == 4 and frames_u8.shape[-1] == 3
+    T, H, W, _ = frames_u8.shape
+    out = torch.empty((1, T, 3, H, W), device=frames_u8.device, dtype=torch.float32)
+    _ck(lib().vmgb_frames_u8_to_f32(frames_u8.data_ptr(), out.data_ptr(), T, H, W, int(reverse_channels), _stream()), 'vmgb_frames_u8_to_f32')
+    return out
+
+
+def frames_f32_to_u8(frames, reverse_channels=False, out=None):
+    """fp32 [T,3,H,W] (or [1,T,3,H,W]) -> uint8 [T,H,W,3]: clamp, *255, round half to even (Tester.py:249-250)."""
+    require_device()
+    if frames.dim() == 5:
+        assert frames.shape[0] == 1
+        frames = frames[0]
+    assert frames.dtype == torch.float32 and frames.is_contiguous() and frames.shape[1] == 3
+    T, _, H, W = frames.shape
+    if out is None:
+        out = torch.empty((T, H, W, 3), device=frames.device, dtype=torch.uint8)
+    _ck(lib().vmgb_frames_f32_to_u8(frames.data_ptr(), out.data_ptr(), T, H, W, int(reverse_channels), _stream()), 'vmgb_frames_f32_to_u8')
+    return out
+
+
+def blend_accumulate_(E, count, patch, t0, h0, w0, zero_t=(0, 0), zero_h=(0, 0), zero_w=(0, 0)):
+    require_device()
+    B, Tp, C, ph, pw = patch.shape
+    _, Te, _, He, We = E.shape
+    assert patch.dtype == torch.float32 and E.dtype == torch.float32 and patch.is_contiguous() and E.is_contiguous()
+    assert E.shape[0] == B and E.shape[2] == C
+    assert count is None or (count.dtype == torch.float32 and count.is_contiguous() and tuple(count.shape) == (Te, He, We))
+    _ck(lib().vmgb_blend_accumulate(patch.data_ptr(), E.data_ptr(), _ptr(count), B, Tp, C, ph, pw, Te, He, We, t0, h0, w0,
+                                    zero_t[0], zero_t[1], zero_h[0], zero_h[1], zero_w[0], zero_w[1], _stream()), 'vmgb_blend_accumulate')
+    return E
+
+
+def blend_normalize_(E, count):
+    require_device()
+    B, Te, C, He, We = E.shape
+    assert tuple(count.shape) == (Te, He, We) and count.dtype == torch.float32 and count.is_contiguous() and E.is_contiguous()
+    _ck(lib().vmgb_blend_normalize(E.data_ptr(), count.data_ptr(), B, Te, C, He, We, _stream()), 'vmgb_blend_normalize')
+    return E
+
+
+def blend_finalize_u8(E, count=None, reverse_channels=False):
+    require_device()
+    B, T, C, H, W = E.shape
+    assert B == 1 and C == 3 and E.dtype == torch.float32 and E.is_contiguous()
+    assert count is None or (tuple(count.shape) == (T, H, W) and count.dtype == torch.float32 and count.is_contiguous())
+    out = torch.empty((T, H, W, 3), device=E.device, dtype=torch.uint8)
+    _ck(lib().vmgb_blend_finalize_u8(E.data_ptr(), _ptr(count), out.data_ptr(), T, H, W, int(reverse_channels), _stream()),
+        'vmgb_blend_finalize_u8')
+    return out
+
+
+def augment(x, hflip, vflip, transpose):
+    """[..., H, W] fp32 -> flips / transpose of Tester.augment (applied in the reference's order)."""
+    require_device()
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    H, W = x.shape[-2:]
+    planes = x.numel() // (H * W)
+    out = torch.empty(tuple(x.shape[:-2]) + ((W, H) if transpose else (H, W)), device=x.device, dtype=torch.float32)
+    _ck(lib().vmgb_augment(x.data_ptr(), out.data_ptr(), planes, H, W, int(hflip), int(vflip), int(transpose), _stream()), 'vmgb_augment')
+    return out
+
+
+def _scratch(n_img, H, W, n_planes, device):
+    n = int(lib().vmgb_metrics_scratch_doubles(n_img, H, W, n_planes))
+    return torch.empty(n, device=device, dtype=torch.float64)
+
+
+def sse_u8(a, b):
+    """Exact integer sum of squared differences of two uint8 tensors (python int; host sync)."""
+    require_device()
+    assert a.dtype == torch.uint8 and b.dtype == torch.uint8 and a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    acc = torch.zeros(1, device=a.device, dtype=torch.int64)
+    _ck(lib().vmgb_sse_u8(a.data_ptr(), b.data_ptr(), a.numel(), acc.data_ptr(), _stream()), 'vmgb_sse_u8')
+    return int(acc.item())
+
+
+def sse_f32(a, b, clamp01=False):
+    require_device()
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    out = torch.empty(1, device=a.device, dtype=torch.float64)
+    _ck(lib().vmgb_sse_f32(a.data_ptr(), b.data_ptr(), a.numel(), int(clamp01), _scratch(1, 11, 11, 1, a.device).data_ptr(), out.data_ptr(),
+                           _stream()), 'vmgb_sse_f32')
+    return out
+
+
+def sse_f64(a, b):
+    require_device()
+    assert a.dtype == torch.float64 and b.dtype == torch.float64 and a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    out = torch.empty(1, device=a.device, dtype=torch.float64)
+    _ck(lib().vmgb_sse_f64(a.data_ptr(), b.data_ptr(), a.numel(), _scratch(1, 11, 11, 1, a.device).data_ptr(), out.data_ptr(), _stream()),
+        'vmgb_sse_f64')
+    return out
+
+
+def rgb_to_y(rgb_u8):
+    """uint8 [..., 3] RGB -> float64 [...] luma of skimage.color.rgb2ycbcr."""
+    require_device()
+    assert rgb_u8.dtype == torch.uint8 and rgb_u8.is_contiguous() and rgb_u8.shape[-1] == 3
+    y = torch.empty(rgb_u8.shape[:-1], device=rgb_u8.device, dtype=torch.float64)
+    _ck(lib().vmgb_rgb_to_y(rgb_u8.data_ptr(), y.data_ptr(), y.numel(), _stream()), 'vmgb_rgb_to_y')
+    return y
+
+
+def ssim(a, b, window11):
+    """a, b: uint8 [n,H,W,3] (mean over channels) or float64 [n,H,W]; window11: 11 python floats.  -> fp64 [n] (device)."""
+    require_device()
+    assert a.shape == b.shape and a.dtype == b.dtype and a.is_contiguous() and b.is_contiguous()
+    if a.dtype == torch.uint8:
+        n, H, W, P = a.shape
+        dt = 0
+    else:
+        assert a.dtype == torch.float64
+        n, H, W = a.shape
+        P, dt = 1, 1
+    win = (ctypes.c_double * 11)(*[float(v) for v in window11])
+    out = torch.empty(n, device=a.device, dtype=torch.float64)
+    _ck(lib().vmgb_ssim(a.data_ptr(), b.data_ptr(), dt, n, H, W, P, ctypes.cast(win, ctypes.c_void_p), _scratch(n, H, W, P, a.device).data_ptr(),
+                        out.data_ptr(), _stream()), 'vmgb_ssim')
     return out
