@@ -100,6 +100,21 @@ int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2, int n_src
                         int act, float act_alpha, float out_scale, int epi, float res_scale,
                         int pixel_shuffle, int variant, void* stream);
 
+/* ---- resblock_chain: the residual-block chain of the trajectory module as ONE persistent kernel -------------------
+ * trajectory.py:16-52 (ResidualBlocksWithInputConv.main[2]) / :165-221 (ResidualBlockNoBN0):
+ *     for each of n_blocks blocks:  y <- y + res_scale * conv2(relu(conv1(y)))        (3x3, C -> C, zero padding)
+ * i.e. 2*n_blocks dependent convolutions per call (30 per trajectory step).  bf16 channels-last tensors [n_img,H,W,C]
+ * with pitch C.  y_inout holds the chain input (the output of the input conv) and is OVERWRITTEN; y_alt and t_tmp are
+ * scratch tensors of the same size; the result lands in `out`.
+ * w_layers: bf16 [2*n_blocks][9][C][Kp] -- the vmgb_pack_weight_tc layouts of conv1, conv2 of block 0, 1, ... back to
+ * back; bias_layers: fp32 [2*n_blocks][C].
+ * flags / flags_next: two DIFFERENT arrays of n_img * ceil(H/16) * (W/16) 32-bit counters.  `flags` must be all zero on
+ * entry; the kernel leaves it dirty and zeroes `flags_next`, so consecutive calls alternate the two arrays.
+ * Cross-tile (halo) dependencies between layers are tracked through these counters instead of grid barriers.
+ * Takes C % 16 == 0, C <= 128, W % 16 == 0; VMGB_EUNSUPPORTED otherwise (the caller issues vmgb_conv2d_nhwc_tc per layer). */
+int vmgb_resblock_chain(void* y_inout, void* y_alt, void* t_tmp, void* out, const void* w_layers, int Kp, const float* bias_layers,
+                        void* flags, void* flags_next, int n_img, int H, int W, int C, int n_blocks, float res_scale, void* stream);
+
 /* OIHW fp32 conv weight [Cout][Cin/groups][R][S] (or Linear [Cout][Cin], R=S=1) -> packed layouts.
  * tc layout: input channel ci of group g is stored at k = ((g*Cin/groups) % 8) + ci, so
  * Kp >= Cin/groups + max_g((g*Cin/groups) % 8), Kp % 16 == 0. */

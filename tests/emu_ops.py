@@ -367,3 +367,27 @@ def sse_f32(a, b, clamp01=False):
 def blend_finalize_u8(E, count=None, reverse_channels=False):
     v = E if count is None else E / count[None, :, None]
     return frames_f32_to_u8(v, reverse_channels)
+
+
+# ---- residual-block chain (same host-side contract as vmg_b200.ops) ---------------------------------------------
+class PackedChain:
+    pass
+
+
+def pack_resblock_chain(layers):
+    pc = PackedChain()
+    pc.layers = list(layers)
+    pc.n_blocks = len(pc.layers) // 2
+    return pc
+
+
+def chain_flags(y):
+    return None
+
+
+def resblock_chain(y, pc, res_scale, out, flags, flags_next, scratch=None):
+    nb = len(pc.layers) // 2
+    for k in range(nb):
+        t = conv2d(y, pc.layers[2 * k], act=ACT_RELU)
+        y = conv2d(t, pc.layers[2 * k + 1], epi=EPI_RESADD, res=y, res_scale=res_scale, out=out if k == nb - 1 else None)
+    return y

@@ -276,7 +276,7 @@ def test_spynet_helpers_and_io():
         r8, ru = emu.spynet_level_input(r0, fc, (T - 1) * B, B, direction)
         close(fu, ru, 2e-5)
         close(o8, r8, 1e-4)
-    o8, fu = ops.spynet_level_input(p0, None, (T - 1) * B, B, 0)
+    o8, fu = ops.spynet_level_input(p0, None, (T - 1) * B, B, 0, semantics=ops.COORD_ATEN_CPU)
     r8, ru = emu.spynet_level_input(r0, None, (T - 1) * B, B, 0)
     close(o8, r8, 1e-5)
     close(ops.flow_resize(fc.to(DEV), 40, 44), emu.flow_resize(fc, 40, 44), 2e-5)

@@ -19,7 +19,7 @@ def main():
     a = ap.parse_args()
     from vmg_b200.model import VMG
     import vmg_b200.model as vm
-    yml, B, T, H, W = bench.WORKLOADS[a.workload]
+    _kind, yml, B, T, H, W = bench.WORKLOADS[a.workload]
     torch.manual_seed(0)
     m = VMG(**bench.model_kwargs(yml), precision='bf16').eval().cuda()
     m.num_out_frames = T

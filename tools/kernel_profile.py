@@ -20,7 +20,7 @@ def main():
     ap.add_argument('--out', default=None)
     a = ap.parse_args()
     from vmg_b200.model import VMG
-    yml, B, T, H, W = bench.WORKLOADS[a.workload]
+    _kind, yml, B, T, H, W = bench.WORKLOADS[a.workload]
     torch.manual_seed(0)
     m = VMG(**bench.model_kwargs(yml), precision=a.precision).eval().cuda()
     m.num_out_frames = T

@@ -23,7 +23,7 @@ def main():
     ap.add_argument('--steps', type=int, default=2)
     a = ap.parse_args()
     from vmg_b200.model import VMG
-    yml, B, T, H, W = bench.WORKLOADS[a.workload]
+    _kind, yml, B, T, H, W = bench.WORKLOADS[a.workload]
     kw = bench.model_kwargs(yml)
     torch.manual_seed(0)
     sd = {k: v.clone().cuda() for k, v in VMG(**kw).state_dict().items()}

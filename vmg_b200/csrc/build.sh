@@ -4,14 +4,14 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -cudart static"
-SRCS="api.cu conv_generic.cu conv_tc.cu elementwise.cu warp.cu ltam.cu evalpath.cu"
+SRCS="api.cu conv_generic.cu conv_tc.cu elementwise.cu warp.cu ltam.cu evalpath.cu resblock_chain.cu"
 mkdir -p build
 OBJS=""
 PIDS=""
 for s in $SRCS; do
   [ -f "$s" ] || continue
   o=build/${s%.cu}.o
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ../../include/vmgb.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ tc_ptx.cuh -nt "$o" ] || [ ../../include/vmgb.h -nt "$o" ]; then
     echo "nvcc $s"
     $NVCC $FLAGS ${VMGB_PTXAS_V:+-Xptxas -v} -c "$s" -o "$o" &
     PIDS="$PIDS $!"

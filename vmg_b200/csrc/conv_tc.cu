@@ -15,6 +15,7 @@
 // K = taps x input channels.  A Linear is the R=S=1 case over a [1,1,rows,K] "image" (tile 1 x 128).
 // Replaces the cuDNN / cuBLAS calls behind nn.Conv2d / nn.Linear on the VMG path.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include <cuda.h>
 #include <mutex>
 #include <cstdlib>
@@ -39,176 +40,6 @@ struct TcP {
   int dbg;                                     // bottleneck probes (tools/microbench.py): 1 = no MMA, 2 = no drain, 4 = no activation loads
 };
 
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  uint32_t spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) break;
-    if (++spins > (1u << 21)) __trap();     // a lost arrival becomes an error (after a few seconds: try_wait itself blocks for a while), never a hang
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
-}
-// programmatic dependent launch: the next kernel of the stream may start its prologue (barriers, TMEM, weight loads)
-// while this one drains; it must not touch anything a predecessor writes (or still reads) before pdl_wait()
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// ---- CTA-pair (cta_group::2) forms: one MMA spans the two SMs of a TPC (M = 256), each CTA holds its own 128
-// rows of A and HALF of the B rows; barriers of the pair live in the leader CTA (rank 0)
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  // default .release.cta semantics (what the accumulator hand-back needs after tcgen05.fence::before_thread_sync);
-  // .release.cluster compiles to MEMBAR.ALL.GPU, which waits for every global store of the epilogue still in flight
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// predicated forms: the surrounding code stays warp-uniform (descriptors in uniform registers, no R2UR per operand);
-// `issue` is this lane's elect.sync result
-__device__ __forceinline__ void umma_f16_2sm_if(uint32_t issue, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
-}
-// same with the descriptors as (low, high) 32-bit halves: the high words (stride, version, swizzle mode) are loop
-// constants and the low words (start address) advance by immediates, ~5 instructions per MMA instead of ~19
-__device__ __forceinline__ void umma_f16_2sm_if_lh(uint32_t issue, uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                                   uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "setp.ne.b32 q, %7, 0;\n\t"
-      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm_if(uint32_t issue, uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %2, 0;\n\t"
-      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
-      ::"r"(bar), "h"(mask), "r"(issue) : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-// one elected lane of a converged warp (keeps the surrounding code warp-uniform so that descriptors and
-// barrier addresses live in uniform registers; a `lane == 0` branch makes ptxas wrap every UTCHMMA / UTMALDG
-// in an R2UR.BROADCAST "waterfall" loop, ~4x slower issue)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// same, with an explicit stride between 8-row groups (multiple of 1024 B)
-__device__ __forceinline__ uint64_t smem_desc_sw128_sbo(uint32_t addr, uint32_t sbo) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-// SWIZZLE_128B, K-major operand: 8-row groups 1024 B apart (SBO), LBO unused (=1), descriptor version 1
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-
-// SWIZZLE_32B, K-major operand of exactly one K = 16 slice: rows of 32 B, 8-row groups 256 B apart
-__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)6 << 61);
-}
-
 constexpr int A_STAGE_BYTES = 128 * 128;   // 128 pixels x 64 bf16
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;            // column offset of the second accumulator
@@ -222,24 +53,6 @@ constexpr int ACC_STRIDE = 256;            // column offset of the second accumu
 //   2. reads the bias from shared memory (staged once per (group, N tile)),
 //   3. tcgen05.ld -> bias / activation / scale / residual / gate / pixel shuffle -> 16-byte stores.
 // ---------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
-}
-__device__ __forceinline__ uint4 pack8(const float* f) {
-  uint4 q;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-  return q;
-}
 
 // exact-erf GELU with erf from Abramowitz & Stegun 7.1.28: erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16, |error| <= 3e-7
 // (far below bf16 resolution), z = |x|/sqrt(2).  One MUFU (rcp.approx) + ~14 FMA-class operations per element; the
@@ -260,6 +73,41 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float erf_abs = 1.f - r;                             // erf(|x|/sqrt2)
   const float hx = 0.5f * x;
   return fmaf(fabsf(hx), erf_abs, hx);                      // 0.5*x*(1 + sign(x)*erf_abs) = hx + |hx|*erf_abs
+}
+
+// Packed form (Blackwell FFMA2 / FMUL2: one instruction per TWO fp32 lanes, same rounding as the scalar ops): the
+// polynomial, its 16th power and the final scale run on pairs, only |x| (source modifier) and the MUFU stay scalar --
+// ~9 instead of ~17 issue slots per element in the issue-bound FFN fc1 epilogue.  Bit-identical to gelu_erf_fast.
+__device__ __forceinline__ unsigned long long pack_f2(float a, float b) {
+  return (unsigned long long)__float_as_uint(a) | ((unsigned long long)__float_as_uint(b) << 32);
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
+  const unsigned long long z = pack_f2(fabsf(x0) * 0.70710678118654752440f, fabsf(x1) * 0.70710678118654752440f);
+  unsigned long long p = fma2(z, pack_f2(0.0000430638f, 0.0000430638f), pack_f2(0.0002765672f, 0.0002765672f));
+  p = fma2(z, p, pack_f2(0.0001520143f, 0.0001520143f));
+  p = fma2(z, p, pack_f2(0.0092705272f, 0.0092705272f));
+  p = fma2(z, p, pack_f2(0.0422820123f, 0.0422820123f));
+  p = fma2(z, p, pack_f2(0.0705230784f, 0.0705230784f));
+  p = fma2(z, p, pack_f2(1.f, 1.f));
+  p = mul2(p, p); p = mul2(p, p); p = mul2(p, p); p = mul2(p, p);                     // ^16
+  float r0, r1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(__uint_as_float((uint32_t)p)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(__uint_as_float((uint32_t)(p >> 32))));
+  const unsigned long long e = fma2(pack_f2(r0, r1), pack_f2(-1.f, -1.f), pack_f2(1.f, 1.f));      // erf(|x|/sqrt2) = 1 - r
+  const unsigned long long h = mul2(pack_f2(x0, x1), pack_f2(0.5f, 0.5f));
+  const float h0 = __uint_as_float((uint32_t)h), h1 = __uint_as_float((uint32_t)(h >> 32));
+  x0 = fmaf(fabsf(h0), __uint_as_float((uint32_t)e), h0);
+  x1 = fmaf(fabsf(h1), __uint_as_float((uint32_t)(e >> 32)), h1);
 }
 
 // whether chunk `nb` (first column inside the group) of this pixel can use the vector bf16 residual prefetch
@@ -302,7 +150,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw
       break;
     case VMGB_ACT_GELU:
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = gelu_erf_fast(v[j]);
+      for (int j = 0; j < 16; j += 2) gelu_erf_fast2(v[j], v[j + 1]);
       break;
     case VMGB_ACT_SIGMOID:
 #pragma unroll

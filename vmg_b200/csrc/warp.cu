@@ -126,28 +126,35 @@ __global__ void __launch_bounds__(256) flow_warp_nearest2_kernel(const float* __
 
 // ---------------------------------------------------------------------------------------------
 // flow_warp_fused: ONE launch per trajectory step for both warps that share a flow field (trajectory.py:330-333):
-// the bilinear feature warp (bf16, 8 channels per work item) and the nearest warp of all K tracked locations
-// (one (x, y) pair per work item).  Work item i of pixel p: i < C/8 -> feature group i, else location i - C/8.
+// the bilinear feature warp (bf16, 8 channels per thread) and the nearest warp of all K tracked locations (one (x, y)
+// pair per thread).  Roles are BLOCK-uniform (blocks [0, nb_feat) warp features, the rest locations): mixing both kinds of
+// work items inside a warp made every warp execute both bodies (measured 54 us against 44 us for the two launches).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) flow_warp_fused_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch, const float* __restrict__ flow,
                                                              __nv_bfloat16* __restrict__ out, int out_pitch, const float* __restrict__ loc,
                                                              int loc_in_pitch, float* __restrict__ loc_out, int loc_out_pitch, int K, int n, int h,
-                                                             int w, int C, int sem, long long total) {
-  const int C8 = C >> 3, per = C8 + K;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int item = (int)(i % per); const long long pix = i / per;
+                                                             int w, int C, int sem, int nb_feat) {
+  const long long npix = (long long)n * h * w;
+  if ((int)blockIdx.x >= nb_feat) {
+    const long long total = npix * K, stride = (long long)(gridDim.x - nb_feat) * blockDim.x;
+    for (long long i = (long long)(blockIdx.x - nb_feat) * blockDim.x + threadIdx.x; i < total; i += stride) {
+      const int k = (int)(i % K); const long long pix = i / K;
+      const int px = (int)(pix % w); const long long t = pix / w; const int py = (int)(t % h); const int img = (int)(t / h);
+      const float2 f = *reinterpret_cast<const float2*>(flow + pix * 2);
+      const int sx = (int)rintf(warp_coord((float)px, f.x, w, sem)), sy = (int)rintf(warp_coord((float)py, f.y, h, sem));
+      *reinterpret_cast<float2*>(loc_out + pix * loc_out_pitch + 2 * k) =
+          *reinterpret_cast<const float2*>(loc + (((long long)img * h + sy) * w + sx) * loc_in_pitch + 2 * k);
+    }
+    return;
+  }
+  const int C8 = C >> 3;
+  const long long total = npix * C8, stride = (long long)nb_feat * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c8 = (int)(i % C8); const long long pix = i / C8;
     const int px = (int)(pix % w); const long long t = pix / w; const int py = (int)(t % h); const int img = (int)(t / h);
     const float2 f = *reinterpret_cast<const float2*>(flow + pix * 2);
     const float ix = warp_coord((float)px, f.x, w, sem), iy = warp_coord((float)py, f.y, h, sem);
     const long long ib = (long long)img * h;
-    if (item >= C8) {
-      const int k = item - C8;
-      const int sx = (int)rintf(ix), sy = (int)rintf(iy);
-      *reinterpret_cast<float2*>(loc_out + pix * loc_out_pitch + 2 * k) =
-          *reinterpret_cast<const float2*>(loc + ((ib + sy) * w + sx) * loc_in_pitch + 2 * k);
-      continue;
-    }
-    const int c8 = item;
     const float fx0 = floorf(ix), fy0 = floorf(iy);
     const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
     const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix, wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
@@ -390,10 +397,11 @@ extern "C" int vmgb_flow_warp_fused(const void* x, int x_pitch, const float* flo
   if ((C & 7) || (x_pitch & 7) || (out_pitch & 7) || (((uintptr_t)x | (uintptr_t)out) & 15) || (loc_in_pitch & 1) || (loc_out_pitch & 1) ||
       (((uintptr_t)loc | (uintptr_t)loc_out) & 7))
     return VMGB_EUNSUPPORTED;      // the caller falls back to the two separate launches
-  const long long total = (long long)n * h * w * (C / 8 + K2 / 2);
-  flow_warp_fused_kernel<<<grid_for2(total, 256, 148 * 32), 256, 0, as_stream(stream)>>>(
+  const long long npix = (long long)n * h * w;
+  const int nb_feat = grid_for2(npix * (C / 8), 256, 148 * 24), nb_loc = grid_for2(npix * (K2 / 2), 256, 148 * 8);
+  flow_warp_fused_kernel<<<nb_feat + nb_loc, 256, 0, as_stream(stream)>>>(
       (const __nv_bfloat16*)x, x_pitch, flow, (__nv_bfloat16*)out, out_pitch, loc, loc_in_pitch, loc_out, loc_out_pitch, K2 / 2, n, h, w, C,
-      semantics, total);
+      semantics, nb_feat);
   return check_launch();
 }
 

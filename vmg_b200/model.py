@@ -406,20 +406,28 @@ class VMG(nn.Module):
     # -------------------------------------------------------------------------------------------
     # Trajectory_multi_head (trajectory.py:300-490) + LTAM wins (trajectory.py:672-795)
     # -------------------------------------------------------------------------------------------
-    def _resblocks(self, rb, srcs, out):
+    def _pchain(self, blocks):
+        """Packed weights of the whole residual-block chain (ops.PackedChain), re-packed when any conv changed."""
+        layers = [self._pc(c) for blk in blocks for c in (blk.conv1, blk.conv2)]
+        key = ('chain', id(blocks))
+        ver = tuple(id(q) for q in layers)
+        ent = self._packed.get(key)
+        if ent is None or ent[0] != ver:
+            ent = (ver, _ops.pack_resblock_chain(layers))
+            self._packed[key] = ent
+        return ent[1]
+
+    def _resblocks(self, rb, srcs, out, flags=None, step=0, scratch=None):
         o = _ops
         main = rb.main
         y = o.conv2d(srcs, self._pc(main[0]), act=o.ACT_LRELU, alpha=0.1)
         blocks = main[2]
-        nb = len(blocks)
-        if nb == 0:
+        if len(blocks) == 0:
             out.copy_(y)
             return out
-        for k, blk in enumerate(blocks):
-            t = o.conv2d(y, self._pc(blk.conv1), act=o.ACT_RELU)
-            y = o.conv2d(t, self._pc(blk.conv2), epi=o.EPI_RESADD, res=y, res_scale=self.r_scaling,
-                         out=out if k == nb - 1 else None)
-        return y
+        fl = flags if flags is not None else o.chain_flags(y)
+        f0, f1 = (fl[step & 1], fl[(step + 1) & 1]) if fl is not None else (None, None)
+        return o.resblock_chain(y, self._pchain(blocks), self.r_scaling, out, f0, f1, scratch)
 
     def _trajectory(self, st, x, B, T, flows_f, flows_b):
         """Both sweeps of Trajectory_multi_head share their weights and are independent until the final
@@ -446,6 +454,8 @@ class VMG(nn.Module):
         o.loc_identity_(loc[0], 0)
         cur_loc, K = 0, 0
         prev = None
+        flags = o.chain_flags(fbuf[0])                  # per-pair dependency counters of the persistent resblock-chain kernel
+        scratch = (torch.empty_like(fbuf[0]), torch.empty_like(fbuf[0]))
         for j in range(T):
             is_key = j % stride == 0
             if j == 0:
@@ -460,7 +470,7 @@ class VMG(nn.Module):
                     o.loc_identity_(loc[cur_loc], 2 * K)
             if is_key:
                 K += 1                                  # step j becomes key frame K-1 once fbuf[j] is written
-            prev = self._resblocks(tm.resblocks, (xp[j], feat_in), fbuf[j])
+            prev = self._resblocks(tm.resblocks, (xp[j], feat_in), fbuf[j], flags, j, scratch)
         back, fwd = o.unpair_sweeps(fbuf)               # outputs_back[i] = backward sweep at step T-1-i
         return o.conv2d((back, x, fwd), self._pc(tm.fusion), act=o.ACT_LRELU, alpha=0.1)
 

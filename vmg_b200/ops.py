@@ -163,6 +163,62 @@ def pack_conv(weight, bias, groups=1, tc=False):
     return pc
 
 
+
+class PackedChain:
+    """Kernel-side weights of one residual-block chain: the tcgen05 layouts of conv1, conv2 of block 0, 1, ... back to back
+    (bf16 [2n][9][C][Kp]) and the biases (fp32 [2n][C]); `layers` keeps the per-layer PackedConv for the per-layer path."""
+    __slots__ = ('wtc', 'bias', 'Kp', 'C', 'n_blocks', 'layers')
+
+
+def pack_resblock_chain(layers):
+    """layers: PackedConv of conv1, conv2 of every block in order (all 3x3, C -> C, packed with tc=True)."""
+    pc = PackedChain()
+    pc.layers = list(layers)
+    pc.n_blocks = len(pc.layers) // 2
+    l0 = pc.layers[0]
+    pc.C, pc.Kp = l0.Cout, l0.Kp
+    pc.wtc, pc.bias = None, None
+    ok = all(q.wtc is not None and q.R == 3 and q.S == 3 and q.groups == 1 and q.Cin == pc.C and q.Cout == pc.C and q.Kp == pc.Kp and
+             q.bias is not None for q in pc.layers)
+    if ok and len(pc.layers) == 2 * pc.n_blocks and pc.n_blocks >= 1:
+        pc.wtc = torch.cat([q.wtc for q in pc.layers])
+        pc.bias = torch.stack([q.bias for q in pc.layers]).contiguous()
+    return pc
+
+
+def resblock_chain_supported(pc, y):
+    return (pc.wtc is not None and y.dtype == torch.bfloat16 and y.is_contiguous() and pc.C % 16 == 0 and pc.C <= 128 and
+            y.shape[2] % 16 == 0 and y.shape[1] >= 8 and y.shape[-1] == pc.C)
+
+
+def chain_flags(y):
+    """Two zeroed dependency-counter arrays for vmgb_resblock_chain on tensors shaped like y [n,H,W,C]."""
+    n, H, W, _ = y.shape
+    return torch.zeros((2, n * ((H + 15) // 16) * (W // 16)), device=y.device, dtype=torch.int32)
+
+
+def resblock_chain(y, pc, res_scale, out, flags, flags_next, scratch=None):
+    """y <- y + res_scale * conv2(relu(conv1(y))) for every block of `pc`; y [n,H,W,C] bf16 is consumed (overwritten),
+    the result is written to `out`.  ONE persistent kernel when the shape is supported, else 2 launches per block."""
+    require_device()
+    if resblock_chain_supported(pc, y):
+        n, H, W, C = y.shape
+        y_alt, t_tmp = scratch if scratch is not None else (torch.empty_like(y), torch.empty_like(y))
+        assert out.is_contiguous() and out.shape == y.shape and out.dtype == y.dtype
+        rc = lib().vmgb_resblock_chain(y.data_ptr(), y_alt.data_ptr(), t_tmp.data_ptr(), out.data_ptr(), pc.wtc.data_ptr(), pc.Kp,
+                                       pc.bias.data_ptr(), flags.data_ptr(), flags_next.data_ptr(), n, H, W, C, pc.n_blocks,
+                                       float(res_scale), _stream())
+        if rc == 0:
+            return out
+        if rc != -2:
+            _ck(rc, 'vmgb_resblock_chain')
+    nb = len(pc.layers) // 2
+    for k in range(nb):
+        t = conv2d(y, pc.layers[2 * k], act=ACT_RELU)
+        y = conv2d(t, pc.layers[2 * k + 1], epi=EPI_RESADD, res=y, res_scale=res_scale, out=out if k == nb - 1 else None)
+    return y
+
+
 FALLBACK_LOG = []
 
 
