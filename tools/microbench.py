@@ -131,6 +131,37 @@ def run_rows(iters):
         print(json.dumps({'case': name, 'ms': round(ms, 4), 'GBps': round(nb / ms / 1e6, 1)}), flush=True)
 
 
+def run_chain(iters):
+    """The 15-block residual chain of one trajectory step: ONE persistent kernel vs 30 per-layer launches."""
+    flush = torch.zeros(64 * 1024 * 1024, device=DEV)
+    for n, H, W, C, nb in ((2, 184, 320, 112, 15), (2, 128, 128, 112, 15), (2, 184, 320, 144, 15)):
+        layers = [ops.pack_conv(torch.randn(C, C, 3, 3, device=DEV) * 0.03, torch.randn(C, device=DEV) * 0.1, 1, tc=True) for _ in range(2 * nb)]
+        pc = ops.pack_resblock_chain(layers)
+        x = torch.randn(n, H, W, C, device=DEV).bfloat16()
+        out = torch.empty_like(x)
+        flags = ops.chain_flags(x)
+        scratch = (torch.empty_like(x), torch.empty_like(x))
+        state = {'i': 0}
+
+        def chain():
+            i = state['i']
+            state['i'] += 1
+            ops.resblock_chain(x, pc, 0.1, out, flags[i & 1], flags[(i + 1) & 1], scratch)
+
+        def per_layer():
+            y = x
+            for k in range(nb):
+                t = ops.conv2d(y, layers[2 * k], act=ops.ACT_RELU)
+                y = ops.conv2d(t, layers[2 * k + 1], epi=ops.EPI_RESADD, res=y, res_scale=0.1)
+        fl = 2.0 * n * H * W * C * C * 9 * 2 * nb
+        for name, fn in (('chain', chain), ('per_layer', per_layer)):
+            if name == 'chain' and not ops.resblock_chain_supported(pc, x):
+                continue
+            ms = timeit(fn, iters, flush)
+            print(json.dumps({'case': f'{name}_{n}x{H}x{W}x{C}x{nb}', 'ms': round(ms, 4), 'us_per_layer': round(1e3 * ms / (2 * nb), 2),
+                              'tflops': round(fl / ms / 1e9, 1)}), flush=True)
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('what', nargs='?', default='all')
@@ -142,3 +173,5 @@ if __name__ == '__main__':
         run_conv(a.iters, a.only, tuple(int(v) for v in a.variants.split(',')))
     if a.what in ('rows', 'all'):
         run_rows(a.iters)
+    if a.what in ('chain', 'all'):
+        run_chain(a.iters)
