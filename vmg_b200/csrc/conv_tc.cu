@@ -37,6 +37,7 @@ struct TcP {
   int aux_smem;                                // bytes of the gate-operand staging buffer (GATE epilogue; 0 = off)
   int wst;                                     // 1 = warp-private transposition staging epilogue (run_epilogue_w), 32 KB
   int res_tma;                                 // 1 = residual tile fetched by TMA one item ahead (run_epilogue_rtma, CTA-pair kernel)
+  int zero;                                    // always 0, opaque to the compiler (forces data dependencies, see run_epilogue_rtma)
   int dbg;                                     // bottleneck probes (tools/microbench.py): 1 = no MMA, 2 = no drain, 4 = no activation loads
 };
 
@@ -660,6 +661,10 @@ __device__ __forceinline__ void run_epilogue_rtma(const TcP& p, float* bias_s, u
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[i][1].x), "=r"(rr[i][1].y), "=r"(rr[i][1].z), "=r"(rr[i][1].w) : "r"(rrow + ch * 32 + 16) : "memory");
       }
     }
+    // the loads above must have RETURNED before the box is re-armed: a barrier orders their issue, not their completion, and
+    // with a power-of-two row pitch (NT = 64 / 128: 32-way bank conflicts) they were still queued when the next box landed.
+    // A data-dependent (never taken) branch makes every thread wait for its registers first.
+    if ((or_all8(rr) & (uint32_t)p.zero) != 0u) __trap();
     asm volatile("bar.sync 1, 256;" ::: "memory");      // every thread holds its residual: the buffer can be refilled
     if (issuer_warp && t + step < total) request(t + step);
     mbar_wait(tfull0 + 8 * as, aph);
@@ -1343,7 +1348,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   p.bias = (const float*)bias; p.out = out; p.res = res; p.aux = aux;
   p.out_dt = out_dt; p.out_pitch = out_pitch; p.res_dt = res_dt; p.res_pitch = res_pitch; p.aux_dt = aux_dt; p.aux_pitch = aux_pitch;
   p.act = act; p.alpha = act_alpha; p.out_scale = out_scale; p.epi = epi; p.res_scale = res_scale; p.ps = pixel_shuffle;
-  p.dbg = 0; p.wst = 0; p.res_tma = 0;
+  p.dbg = 0; p.zero = 0; p.wst = 0; p.res_tma = 0;
   p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0; p.res_smem = 0; p.out_smem = 0; p.aux_smem = 0;
   const int budget = g_smem_optin - 1024 - 512 - 1024;     // alignment slack, barriers, bias staging
 

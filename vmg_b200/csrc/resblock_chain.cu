@@ -17,8 +17,17 @@
 //   * the 129 KB weight slice of the next layer streams into shared memory as soon as the last MMA of the current layer
 //     has retired (tcgen05.commit -> wfree barrier), box by box in consumption order, while the epilogue drains;
 //   * the residual tile of conv2 arrives by TMA one tile ahead (first tile of a layer: during the preceding conv1 layer).
+// Warp roles (14 warps): 0 activation producer, 1 MMA issuer (leader CTA), 2 TMEM allocation then DEPENDENCY CHECKER,
+// 3 weight (+ bias) producer, 4-11 epilogue, 12 PUBLISHER, 13 residual requester.  The epilogue warps never meet at a
+// block barrier and never execute a GPU-scope fence: each warp bumps a shared-memory counter when its stores of a tile are
+// issued (pub_cnt) / when it holds its residual pieces in registers (res_cnt); the publisher turns "8 warps done" into ONE
+// red.release.gpu on flags[pair] (the MEMBAR.ALL.GPU + L1 invalidation of that release took 40 % of the time of the epilogue
+// warp that used to execute it, with the other seven waiting for it at the next barrier -- profiles/r2_chain_ncu.md), the
+// requester re-arms the residual box, and the checker polls the 9 neighbour flags of every tile ahead of the producer and
+// posts its progress in shared memory (the producer used to spend 2/3 of its time in ld.acquire.gpu round trips).
 // Cross-proxy ordering: outputs are written with generic stores and re-read by TMA (async proxy) from other SMs:
-// writer = bar.sync (epilogue threads) + __threadfence + red.release.gpu; reader = ld.acquire.gpu + fence.proxy.async.
+// writer = __syncwarp + red.release.cta (epilogue warp) -> ld.acquire.cta + red.release.gpu (publisher);
+// reader = ld.acquire.gpu (checker) -> st.release.cta / ld.acquire.cta -> fence.proxy.async (producer) -> TMA.
 // Every spin loop traps after ~2 s: a lost dependency becomes an error, never a hang.
 #include "tc_ptx.cuh"
 #include <mutex>
@@ -35,9 +44,10 @@ struct ChainP {
   unsigned* flags;                    // this launch's per-pair counters (zero on entry)
   unsigned* flags_next;               // the next launch's counters: zeroed here
   float res_scale;
+  int zero;                           // always 0, opaque to the compiler (forces a data dependency)
 };
 
-constexpr int CH_THREADS = 384;
+constexpr int CH_THREADS = 448;
 constexpr int CH_MAX_BOXES = 18;       // 9 taps x 2 K blocks
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
@@ -49,6 +59,25 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// shared-memory progress counters between the warps of one CTA
+__device__ __forceinline__ unsigned lds_acquire_cta(uint32_t a) {
+  unsigned v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_release_cta(uint32_t a, unsigned v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void reds_release_cta_add(uint32_t a, unsigned v) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+// all lanes spin until the counter at `a` reaches `target` (monotonic counters: no phase to miss)
+__device__ __forceinline__ void spin_counter(uint32_t a, unsigned target) {
+  const long long t0 = clock64();
+  while ((int)(lds_acquire_cta(a) - target) < 0) {
+    if (clock64() - t0 > (1LL << 32)) __trap();
+  }
+}
 
 // first / end pair of cluster c
 __device__ __forceinline__ void chain_range(const ChainP& p, int c, int& p0, int& p1) {
@@ -83,8 +112,9 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   const uint32_t tfull0 = wfull0 + 8 * CH_MAX_BOXES, tempty0 = tfull0 + 16;
   const uint32_t rfull = tempty0 + 16, wfree = rfull + 8;
   const uint32_t tmem_slot = wfree + 8;
+  const uint32_t dep_ready = tmem_slot + 4, pub_cnt = tmem_slot + 8, res_cnt = tmem_slot + 12;      // progress counters
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  float* bias_s = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));      // [2][128]: layer parity
   const uint32_t res_s = (smem_u32(bias_s) + 1024u + 127u) & ~127u;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -96,6 +126,7 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
     for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 512); }
     mbar_init(rfull, 1);
     mbar_init(wfree, 1);
+    tmem_slot_ptr[1] = 0u; tmem_slot_ptr[2] = 0u; tmem_slot_ptr[3] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -137,19 +168,8 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         const int pair = p0 + chain_order(n_own, s);
         int img, h0, w0;
         tile_of(pair, img, h0, w0);
-        if (l > 0) {
-          // halo dependency: layer l-1 of the 3 x 3 pair neighbourhood is in memory (both tiles of each pair)
-          const int row = pair / p.pairs_w, pc = pair - row * p.pairs_w, th = row - img * p.tiles_h;
-          const int dr = lane / 3 - 1, dc = lane % 3 - 1;
-          const bool act = lane < 9 && th + dr >= 0 && th + dr < p.tiles_h && pc + dc >= 0 && pc + dc < p.pairs_w;
-          const unsigned* f = p.flags + (act ? (row + dr) * p.pairs_w + pc + dc : pair);
-          const unsigned need = 2u * (unsigned)l;
-          const long long t0 = clock64();
-          while (true) {
-            const unsigned v = act ? ld_acquire_gpu(f) : need;
-            if (__all_sync(0xffffffffu, v >= need)) break;
-            if (clock64() - t0 > (1LL << 32)) __trap();
-          }
+        if (l > 0) {                                  // halo dependency, resolved ahead of time by the checker warp
+          spin_counter(dep_ready, (unsigned)(l * n_own + s + 1));
           fence_proxy_async();
         }
         for (int kb = 0; kb < p.nkb; ++kb) {
@@ -168,6 +188,10 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
     const uint32_t wfull0_l = mapa_rank(wfull0, 0);
     for (int l = 0; l < NL; ++l) {
       if (l > 0) mbar_wait(wfree, (uint32_t)((l - 1) & 1));
+      // bias of layer l (its buffer was last read by the epilogue of layer l-2, which every MMA of layer l-1 depended on)
+      for (int c = lane; c < NT; c += 32) bias_s[(l & 1) * 128 + c] = __ldg(p.bias + (long long)l * p.C + c);
+      __threadfence_block();
+      __syncwarp();
       if (elect_one()) {
         for (int kb = 0; kb < p.nkb; ++kb)
           for (int tap = 0; tap < TAPS; ++tap) {
@@ -236,7 +260,61 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
       umma_commit_2sm_if(issue, wfree, (uint16_t)3);        // every MMA of this layer has retired: the weight slice may be replaced
       __syncwarp();
     }
-  } else if (warp >= 4) {
+  } else if (warp == 2) {
+    // ===================== dependency checker (both CTAs): runs ahead of the producer, never blocked by the ring =====================
+    pdl_wait();                                       // this launch's counters were zeroed by the previous launch
+    for (int l = 1; l < NL; ++l) {
+      const unsigned need = 2u * (unsigned)l;         // layer l-1 of the 3 x 3 pair neighbourhood is in memory (both tiles of each pair)
+      for (int s = 0; s < n_own; ++s) {
+        const int pair = p0 + chain_order(n_own, s);
+        const int row = pair / p.pairs_w, pc = pair - row * p.pairs_w, img = row / p.tiles_h, th = row - img * p.tiles_h;
+        const int dr = lane / 3 - 1, dc = lane % 3 - 1;
+        const bool act = lane < 9 && th + dr >= 0 && th + dr < p.tiles_h && pc + dc >= 0 && pc + dc < p.pairs_w;
+        const unsigned* f = p.flags + (act ? (row + dr) * p.pairs_w + pc + dc : pair);
+        const long long t0 = clock64();
+        while (true) {
+          const unsigned v = act ? ld_acquire_gpu(f) : need;
+          if (__all_sync(0xffffffffu, v >= need)) break;
+          if (clock64() - t0 > (1LL << 32)) __trap();
+        }
+        if (lane == 0) sts_release_cta(dep_ready, (unsigned)(l * n_own + s + 1));
+        __syncwarp();
+      }
+    }
+  } else if (warp == 12) {
+    // ===================== publisher (both CTAs): "8 epilogue warps stored (pair, layer l)" -> one release increment of flags[pair] =====================
+    pdl_wait();
+    unsigned done = 0;
+    for (int l = 0; l < NL; ++l)
+      for (int s = 0; s < n_own; ++s) {
+        done += 8u;
+        spin_counter(pub_cnt, done);
+        if (lane == 0) red_release_gpu_add(p.flags + p0 + chain_order(n_own, s), 1u);
+        __syncwarp();
+      }
+  } else if (warp == 13) {
+    // ===================== residual requester (both CTAs): the box of conv2 tile j+1 is requested as soon as tile j's is in registers =====================
+    pdl_wait();
+    unsigned consumed = 0;
+    const uint32_t row_bytes = (uint32_t)NT * 2u;
+    for (int l = 1; l < NL; l += 2) {
+      // the residual of layer l is the block input, written by this CTA's epilogue in layer l-2 (l = 1: the chain input)
+      spin_counter(pub_cnt, 8u * (unsigned)(n_own * (l - 1)));
+      const CUtensorMap* mR = ((l >> 1) & 1) ? &mapR1 : &mapR0;
+      for (int s = 0; s < n_own; ++s) {
+        spin_counter(res_cnt, consumed);                // the previous box has been moved to registers by all 8 warps
+        consumed += 8u;
+        int img, h0, w0;
+        tile_of(p0 + chain_order(n_own, s), img, h0, w0);
+        if (elect_one()) {
+          fence_proxy_async();
+          mbar_expect_tx(rfull, 128u * row_bytes);
+          tma_load_4d(res_s, mR, rfull, 0, w0, h0, img);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
     // ===================== epilogue (8 warps per CTA, each CTA drains its own 128 accumulator rows) =====================
     pdl_wait();
     const int ew = warp - 4, quarter = warp & 3, half = ew >> 2;
@@ -246,27 +324,11 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
     const uint32_t tempty_l = mapa_rank(tempty0, 0);
     uint32_t acc_phase0 = 0, acc_phase1 = 0, rphase = 0;
     int it = 0;
-    const bool issuer_warp = ew == 0;
-    auto request_res = [&](int l, int pair) {            // whole warp 4 calls, one lane issues: residual box of (layer l, pair)
-      int img, h0, w0;
-      tile_of(pair, img, h0, w0);
-      const CUtensorMap* mR = ((l >> 1) & 1) ? &mapR1 : &mapR0;
-      if (elect_one()) {
-        fence_proxy_async();                              // the box was written by this CTA's generic stores two layers ago
-        mbar_expect_tx(rfull, 128u * row_bytes);
-        tma_load_4d(res_s, mR, rfull, 0, w0, h0, img);
-      }
-      __syncwarp();
-    };
     for (int l = 0; l < NL; ++l) {
       const bool conv2 = (l & 1) != 0;
       const int k = l >> 1;
       __nv_bfloat16* outp = conv2 ? (l == NL - 1 ? p.buf[3] : p.buf[(k + 1) & 1]) : p.buf[2];
-      // bias of this layer -> smem (the previous layer's last chunk has been processed by every thread: barrier first)
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int c = ew * 32 + lane; c < NT; c += 256) bias_s[c] = __ldg(p.bias + (long long)l * p.C + c);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (!conv2 && issuer_warp && n_own > 0) request_res(l + 1, p0 + chain_order(n_own, 0));     // lands during this conv1 layer
+      const float* bias_l = bias_s + (l & 1) * 128;     // staged by the weight producer before this layer's first weight box
       for (int s = 0; s < n_own; ++s, ++it) {
         const int pair = p0 + chain_order(n_own, s);
         int img, h0, w0;
@@ -292,8 +354,10 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
               asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[i][1].x), "=r"(rr[i][1].y), "=r"(rr[i][1].z), "=r"(rr[i][1].w) : "r"(rrow + ch * 32 + 16) : "memory");
             }
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");      // every thread holds its residual: the buffer can be refilled
-          if (issuer_warp && s + 1 < n_own) request_res(l, p0 + chain_order(n_own, s + 1));
+          // the loads must have RETURNED in every lane before the box is re-armed (a fence orders issue, not completion of
+          // bank-conflicted shared loads against the TMA write): the warp-wide OR consumes every lane's registers
+          const unsigned z = __reduce_or_sync(0xffffffffu, or_all8(rr) & (uint32_t)p.zero);
+          if (lane == 0) reds_release_cta_add(res_cnt, 1u + z);   // this warp holds its pieces: 8 of these re-arm the box
         }
         mbar_wait(tfull0 + 8 * as, aph);
         tc_fence_after();
@@ -312,7 +376,7 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
             float v[16];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + ch * 16 + 4 * q);
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_l + ch * 16 + 4 * q);
               v[4 * q] = __uint_as_float(work[4 * q]) + b4.x; v[4 * q + 1] = __uint_as_float(work[4 * q + 1]) + b4.y;
               v[4 * q + 2] = __uint_as_float(work[4 * q + 2]) + b4.z; v[4 * q + 3] = __uint_as_float(work[4 * q + 3]) + b4.w;
             }
@@ -336,12 +400,9 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         }
         tc_fence_before();
         mbar_arrive_cluster(tempty_l + 8 * as);
-        // publish (pair, layer l): every epilogue thread's stores are issued -> one release increment per tile
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (ew == 0 && lane == 0) {
-          __threadfence();
-          red_release_gpu_add(p.flags + pair, 1u);
-        }
+        // (pair, layer l): this warp's stores are issued; the publisher releases flags[pair] once all 8 warps are here
+        __syncwarp();
+        if (lane == 0) reds_release_cta_add(pub_cnt, 1u);
       }
     }
   }
@@ -412,7 +473,7 @@ extern "C" int vmgb_resblock_chain(void* y_inout, void* y_alt, void* t_tmp, void
   p.bias = bias_layers;
   p.buf[0] = (__nv_bfloat16*)y_inout; p.buf[1] = (__nv_bfloat16*)y_alt; p.buf[2] = (__nv_bfloat16*)t_tmp; p.buf[3] = (__nv_bfloat16*)out;
   p.flags = (unsigned*)flags; p.flags_next = (unsigned*)flags_next;
-  p.res_scale = res_scale;
+  p.res_scale = res_scale; p.zero = 0;
   const int wbytes = (p.nkb * 9 * p.b_stage_bytes + 1023) / 1024 * 1024;
   const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + 1024 /*bias*/ + 128 + 128 * C * 2 /*residual box*/ + 256;
   p.ra = (g_smem - wbytes - fixed) / p.a_unit_bytes;

@@ -186,6 +186,15 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
 }
+// OR of eight 16-byte registers (used to make a thread wait for the loads that fill them)
+__device__ __forceinline__ uint32_t or_all8(const uint4 (&r)[4][2]) {
+  uint32_t v = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) v |= r[i][j].x | r[i][j].y | r[i][j].z | r[i][j].w;
+  return v;
+}
 __device__ __forceinline__ uint4 pack8(const float* f) {
   uint4 q;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
