@@ -14,8 +14,9 @@
 //     the neighbourhood before it requests the activation boxes of (p, l+1).  Write-after-read hazards on the three
 //     ping-pong buffers are covered by the same flags (a buffer is rewritten two layers after it was read, and layer
 //     l+1 of every reader is a dependency of layer l+2 of the writer);
-//   * the 129 KB weight slice of the next layer streams into shared memory as soon as the last MMA of the current layer
-//     has retired (tcgen05.commit -> wfree barrier), box by box in consumption order, while the epilogue drains;
+//   * the 129 KB weight slice of the next layer streams into shared memory K block by K block: as soon as the last tile of
+//     the current layer has retired its MMAs of block 0 (tcgen05.commit -> wfree0[0]) the next layer's block 0 is loaded,
+//     box by box in consumption order, while block 1 of that tile is still being multiplied and the epilogue drains;
 //   * the residual tile of conv2 arrives by TMA one tile ahead (first tile of a layer: during the preceding conv1 layer).
 // Warp roles (14 warps): 0 activation producer, 1 MMA issuer (leader CTA), 2 TMEM allocation then DEPENDENCY CHECKER,
 // 3 weight (+ bias) producer, 4-11 epilogue, 12 PUBLISHER, 13 residual requester.  The epilogue warps never meet at a
@@ -99,7 +100,7 @@ __device__ __forceinline__ int chain_order(int n, int s) {
 __global__ void __launch_bounds__(CH_THREADS, 1)
 resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                       const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
-                      const __grid_constant__ CUtensorMap mapR0, const __grid_constant__ CUtensorMap mapR1, const ChainP p) {
+                      const __grid_constant__ CUtensorMap mapR0, const __grid_constant__ CUtensorMap mapR1, const __grid_constant__ ChainP p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr int BWX = 10, TAPS = 9, UROWS = 18;
@@ -110,8 +111,8 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   const uint32_t afull0 = bar_base, aempty0 = afull0 + 8 * p.ra;
   const uint32_t wfull0 = aempty0 + 8 * p.ra;
   const uint32_t tfull0 = wfull0 + 8 * CH_MAX_BOXES, tempty0 = tfull0 + 16;
-  const uint32_t rfull = tempty0 + 16, wfree = rfull + 8;
-  const uint32_t tmem_slot = wfree + 8;
+  const uint32_t rfull = tempty0 + 16, wfree0 = rfull + 8;      // wfree0 + 8 * kb: the weight boxes of K block kb may be replaced
+  const uint32_t tmem_slot = wfree0 + 24;      // keeps bias_s (tmem_slot + 16) 16-byte aligned
   const uint32_t dep_ready = tmem_slot + 4, pub_cnt = tmem_slot + 8, res_cnt = tmem_slot + 12;      // progress counters
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));      // [2][128]: layer parity
@@ -125,7 +126,7 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
     for (int i = 0; i < nboxes; ++i) mbar_init(wfull0 + 8 * i, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 512); }
     mbar_init(rfull, 1);
-    mbar_init(wfree, 1);
+    mbar_init(wfree0, 1); mbar_init(wfree0 + 8, 1);
     tmem_slot_ptr[1] = 0u; tmem_slot_ptr[2] = 0u; tmem_slot_ptr[3] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
@@ -187,22 +188,28 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
     // ===================== weight producer (both CTAs): the slice of layer l+1 replaces layer l's as soon as it is free =====================
     const uint32_t wfull0_l = mapa_rank(wfull0, 0);
     for (int l = 0; l < NL; ++l) {
-      if (l > 0) mbar_wait(wfree, (uint32_t)((l - 1) & 1));
-      // bias of layer l (its buffer was last read by the epilogue of layer l-2, which every MMA of layer l-1 depended on)
-      for (int c = lane; c < NT; c += 32) bias_s[(l & 1) * 128 + c] = __ldg(p.bias + (long long)l * p.C + c);
-      __threadfence_block();
-      __syncwarp();
-      if (elect_one()) {
-        for (int kb = 0; kb < p.nkb; ++kb)
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        // the boxes of K block kb are free once the LAST tile of layer l-1 has retired its MMAs of that block: block 0 of
+        // the next layer streams in while block 1 of the last tile is still being multiplied
+        if (l > 0) mbar_wait(wfree0 + 8 * kb, (uint32_t)((l - 1) & 1));
+        if (kb == 0) {
+          // bias of layer l: its buffer was last read by the epilogue of layer l-2, and the last tile of layer l-1 (whose
+          // MMAs have started) depended on the last tile of layer l-2 having been drained
+          for (int c = lane; c < NT; c += 32) bias_s[(l & 1) * 128 + c] = __ldg(p.bias + (long long)l * p.C + c);
+          __threadfence_block();
+          __syncwarp();
+        }
+        if (elect_one()) {
           for (int tap = 0; tap < TAPS; ++tap) {
             const int box = kb * TAPS + tap;
             if (rank == 0) mbar_expect_tx(wfull0 + 8 * box, (uint32_t)(2 * NH * 128));
             tma_load_2d_2sm(w_base + box * p.b_stage_bytes, &mapB, wfull0_l + 8 * box, kb * 64, (l * TAPS + tap) * p.C + (int)rank * NH);
           }
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
-    mbar_wait(wfree, (uint32_t)((NL - 1) & 1));       // the last layer's multicast arrival has landed before this CTA may exit
+    for (int kb = 0; kb < p.nkb; ++kb) mbar_wait(wfree0 + 8 * kb, (uint32_t)((NL - 1) & 1));   // the last multicast arrivals have landed before this CTA may exit
   } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (leader CTA) =====================
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -252,13 +259,12 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
           }
           umma_commit_2sm_if(issue, aempty0 + 8 * ia, (uint16_t)3);
           if (kb == p.nkb - 1) umma_commit_2sm_if(issue, tfull0 + 8 * as, (uint16_t)3);
+          if (s == n_own - 1) umma_commit_2sm_if(issue, wfree0 + 8 * kb, (uint16_t)3);     // last tile of the layer: this K block's weights may be replaced
           __syncwarp();
           accumulate = 1;
           if (++ia == p.ra) { ia = 0; pa ^= 1; }
         }
       }
-      umma_commit_2sm_if(issue, wfree, (uint16_t)3);        // every MMA of this layer has retired: the weight slice may be replaced
-      __syncwarp();
     }
   } else if (warp == 2) {
     // ===================== dependency checker (both CTAs): runs ahead of the producer, never blocked by the ring =====================
