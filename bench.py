@@ -418,6 +418,7 @@ def main():
     if rank == 0:
         recs = []
         real = ops.lib().vmgb_conv2d_nhwc_tc
+        real_chain = ops.lib().vmgb_resblock_chain
 
         def timed(*a):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -426,9 +427,23 @@ def main():
             e.record()
             # C prototype positions 17..24 = n_img,H,W,Cin,Cout,R,S,groups ; 25/27 = act / epilogue
             n_img, h, w, cin, cout, r, s_, g = a[17:25]
-            recs.append((s, e, 2.0 * n_img * h * w * cout * r * s_ * (cin // g), (n_img, h, w, cin, cout, r, g, a[28])))
+            nbytes = 2.0 * n_img * h * w * (cin + cout + (cout if a[28] else 0)) + 2.0 * r * r * (cin // g) * cout
+            recs.append((s, e, 2.0 * n_img * h * w * cout * r * s_ * (cin // g), ('conv', n_img, h, w, cin, cout, r, g), nbytes, 1))
+            return rc
+
+        def timed_chain(*a):
+            # C prototype: y, y_alt, t_tmp, out, w, Kp, bias, flags, flags_next, n_img, H, W, C, n_blocks, res_scale, stream
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = real_chain(*a)
+            e.record()
+            n_img, h, w, c, nb = a[9:14]
+            if rc == 0:       # one launch = 2*nb dependent 3x3 convolutions; compulsory bytes: chain input + output + all weights
+                recs.append((s, e, 2.0 * n_img * h * w * c * 9 * c * 2 * nb, ('chain', n_img, h, w, c, c, 3, 1),
+                             2.0 * n_img * h * w * 2 * c + 2.0 * 2 * nb * 9 * c * c, 2 * nb))
             return rc
         ops.lib().vmgb_conv2d_nhwc_tc = timed
+        ops.lib().vmgb_resblock_chain = timed_chain
         use_graph = model.use_cuda_graph
         model.use_cuda_graph = False          # eager launches so that each one can be bracketed by events
         try:
@@ -436,6 +451,7 @@ def main():
             torch.cuda.synchronize()
         finally:
             ops.lib().vmgb_conv2d_nhwc_tc = real
+            ops.lib().vmgb_resblock_chain = real_chain
             model.use_cuda_graph = use_graph
         peaks = {}
         try:
@@ -446,45 +462,41 @@ def main():
         peak = peaks.get('bf16_tflops_sustained', 1400.0)
         src = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if 'bf16_tflops_sustained' in peaks else 'fallback 1.4 PFLOP/s sustained (of fallback)'
         if recs:
-            # group the tcgen05 convolution launches by shape; the dominant kernel = the group with the most device time
-            groups = {}
-            for s, e, fl, key in recs:
-                gr = groups.setdefault(key, [0, 0.0, 0.0])
-                gr[0] += 1
-                gr[1] += s.elapsed_time(e)
-                gr[2] += fl
-            all_ms = sum(v[1] for v in groups.values())
-            all_fl = sum(v[2] for v in groups.values())
-            # the two epilogue flavours of the trajectory resblock conv (conv1: ReLU store, conv2: residual add) are one kernel
+            # group the tcgen05 launches by (kernel family, shape); the dominant kernel = the group with the most device time
+            # (the two epilogue flavours of a convolution shape -- ReLU store / residual add -- are one kernel)
             by_shape = {}
-            for key, v in groups.items():
-                b = by_shape.setdefault(key[:7], [0, 0.0, 0.0, 0.0])
-                b[0] += v[0]; b[1] += v[1]; b[2] += v[2]
-                ni, hh, ww, ci, co, rr, gg, ep = key      # bf16 activations in + out (+ residual) and the weights, once per launch
-                b[3] += v[0] * (2.0 * ni * hh * ww * (ci + co + (co if ep else 0)) + 2.0 * rr * rr * (ci // gg) * co)
+            for s, e, fl, key, nbytes, layers in recs:
+                b = by_shape.setdefault(key, [0, 0.0, 0.0, 0.0, layers])
+                b[0] += 1; b[1] += s.elapsed_time(e); b[2] += fl; b[3] += nbytes
+            all_ms = sum(v[1] for v in by_shape.values())
+            all_fl = sum(v[2] for v in by_shape.values())
             dom_key, dom = max(by_shape.items(), key=lambda kv: kv[1][1])
             ach = dom[2] / (dom[1] * 1e-3) / 1e12
-            n_img, h, w, cin, cout, r, g = dom_key
+            fam, n_img, h, w, cin, cout, r, g = dom_key
+            if fam == 'chain':
+                kname = 'resblock_chain_kernel'
+            else:
+                kname = 'conv3x3_ws2_kernel' if (r == 3 and cin // g <= 192) else 'conv_tc_kernel'
             traffic, traffic_src = None, None
             for capname in ('r2_dominant_kernel_ncu.json', 'r1_dominant_kernel_ncu.json'):
-                try:                              # dram bytes per launch of the same shape from the committed ncu capture
+                try:                              # dram bytes per launch of the same kernel and shape from the committed ncu capture
                     cap = json.load(open(os.path.join(ROOT, 'profiles', capname)))
-                    if cap.get('shape') == [n_img, h, w, cin, cout, r, g]:
+                    if cap.get('shape') == [n_img, h, w, cin, cout, r, g] and cap.get('kernel', kname) == kname:
                         traffic = cap['dram_bytes_read'] + cap['dram_bytes_write']
                         traffic_src = 'profiles/' + capname
                         break
                 except Exception:
                     pass
-            kname = 'conv3x3_ws2_kernel' if (r == 3 and cin // g <= 192) else 'conv_tc_kernel'
-            roofline = {'kernel': kname, 'shape': {'n_img': n_img, 'H': h, 'W': w, 'Cin': cin, 'Cout': cout, 'R': r, 'groups': g},
+            roofline = {'kernel': kname, 'shape': {'n_img': n_img, 'H': h, 'W': w, 'Cin': cin, 'Cout': cout, 'R': r, 'groups': g,
+                                                   'dependent_conv_layers_per_launch': dom[4]},
                         'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
                         'traffic': traffic, 'traffic_source': traffic_src,
                         'algorithmic_bytes_per_launch': dom[3] / dom[0],
                         'launches': dom[0], 'us_per_launch': 1e3 * dom[1] / dom[0], 'kernel_ms_per_step': dom[1],
                         'share_of_step': dom[1] / ms_step, 'algorithmic_tflop_per_launch': dom[2] / dom[0] / 1e12,
-                        'all_tcgen05_convs': {'launches': len(recs), 'ms_per_step': all_ms, 'achieved': all_fl / (all_ms * 1e-3) / 1e12,
-                                              'share_of_step': all_ms / ms_step},
-                        'timing': 'CUDA events around every launch of one eager forward (graphs off) on the launching stream',
+                        'all_tcgen05_launches': {'launches': len(recs), 'ms_per_step': all_ms, 'achieved': all_fl / (all_ms * 1e-3) / 1e12,
+                                                 'share_of_step': all_ms / ms_step},
+                        'timing': 'CUDA events around every tcgen05 launch of one eager forward (graphs off) on the launching stream',
                         'peak_source': src}
     # ---- the reference's own arithmetic on this GPU + parity of the benched output (rank 0, N = 1 only)
     gpu_reference, parity = None, {'finite': finite}

@@ -115,6 +115,24 @@ int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2, int n_src
 int vmgb_resblock_chain(void* y_inout, void* y_alt, void* t_tmp, void* out, const void* w_layers, int Kp, const float* bias_layers,
                         void* flags, void* flags_next, int n_img, int H, int W, int C, int n_blocks, float res_scale, void* stream);
 
+/* ---- tab_mix: the Morph-FC mixing half of a TAB as two launches of one persistent tcgen05 kernel ---------------------
+ * function.py:743-805 (Enhanced_MorphFCs_decay.forward after the in-place decay) inside TAB.forward (function.py:1212-1215):
+ *     xn = LayerNorm(x) (norm2, eps) ; h = ReLU(MorphFC_H(xn)) / C ; w = ReLU(MorphFC_W(xn)) / C ; c = ReLU(Linear_C(xn)) / C
+ *     a = softmax_3(reweight(mean_{t,h,w}(h + w + c))) ; z = proj(a0.h + a1.w + a2.c) ; out = x + m_scaling * (xn + z) * tanh(z)
+ * x / out: bf16 channels-last, time-major [n_img = T*B, H, W, C] (image i belongs to batch sample i % B).
+ * w_h, w_w, w_c, w_p: vmgb_pack_weight_tc layouts ([C][Kp] bf16, K-major) of mlp_h[0] (already decayed), mlp_w[0], mlp_c[0], proj;
+ * b_*: fp32 [C] or NULL.
+ * phase 0: accumulates sum over the valid pixels of (h + w + c) per (batch sample, channel) into acc [B][C], 64-bit 2^-24
+ *          fixed point (zero it first; vmgb_fixsum_finalize turns it into the fp32 mean); w_p, a, out unused.
+ * phase 1: a = fp32 [B][3][C] branch weights; writes out (must not alias x).
+ * Takes chunk_h = chunk_w = chunk = 8 and C in {64, 112} (the level-0 stages of VMG-REDS); VMGB_EUNSUPPORTED otherwise
+ * (the caller issues layernorm / morph_permute / linears / channel_sum / mix3 / gated projection separately). */
+int vmgb_tab_mix(const void* x, const float* ln_g, const float* ln_b, float eps, const void* w_h, const void* w_w, const void* w_c,
+                 const void* w_p, int Kp, const float* b_h, const float* b_w, const float* b_c, const float* b_p, int phase,
+                 void* acc, const float* a, void* out, float m_scaling, int n_img, int B, int H, int W, int C, int chunk, void* stream);
+/* out[i] = acc[i] * 2^-24 * scale  (acc: the signed 64-bit fixed-point sums of vmgb_tab_mix phase 0 / vmgb_channel_sum) */
+int vmgb_fixsum_finalize(const void* acc, float* out, int n, float scale, void* stream);
+
 /* OIHW fp32 conv weight [Cout][Cin/groups][R][S] (or Linear [Cout][Cin], R=S=1) -> packed layouts.
  * tc layout: input channel ci of group g is stored at k = ((g*Cin/groups) % 8) + ci, so
  * Kp >= Cin/groups + max_g((g*Cin/groups) % 8), Kp % 16 == 0. */

@@ -17,16 +17,26 @@ for i, h in enumerate(hdr):
         print(f'{h:75s} {rows[1][i]:>10s} ' + ' | '.join(r[i] for r in rows[2:]))
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hidx = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
-if not hidx:
-    sys.exit(0)
-h = rows[hidx[kidx]]
-end = hidx[kidx + 1] - 1 if kidx + 1 < len(hidx) else len(rows)
-body = [r for r in rows[hidx[kidx] + 1:end] if len(r) == len(h)]
+# sections: a "Kernel Name" row, then a header row starting with "Address", then one row per SASS instruction
+secs = []
+for i, r in enumerate(rows):
+    if r and r[0] == 'Kernel Name':
+        secs.append([r[1], None, None])
+    elif r and r[0] == 'Address' and secs and secs[-1][1] is None:
+        secs[-1][1] = i
+for k, sc in enumerate(secs):
+    sc[2] = (secs[k + 1][1] - 2) if k + 1 < len(secs) and secs[k + 1][1] else len(rows)
+secs = [sc for sc in secs if sc[1] is not None]
+if len(sys.argv) <= 3:
+    for k, sc in enumerate(secs):
+        print(f'section {k}: {sc[0][:100]}')
+name, h0, end = secs[kidx]
+h = rows[h0]
+body = [r for r in rows[h0 + 1:end] if len(r) == len(h)]
 ci = {n: i for i, n in enumerate(h)}
 stalls = [n for n in h if n.startswith('stall_') and 'Not Issued' not in n]
-tot = sum(int(r[ci['# Samples']] or 0) for r in body)
-print(f'\nkernel #{kidx}: {tot} stall samples over {len(body)} instructions')
+tot = sum(int(r[ci['# Samples']] or 0) for r in body) or 1
+print(f'\nsection {kidx}: {name[:90]}: {tot} stall samples over {len(body)} instructions')
 agg = {n: sum(int(r[ci[n]] or 0) for r in body) for n in stalls}
 print('by reason:', ', '.join(f'{k[6:]} {100 * v / tot:.1f}%' for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]))
 for r in sorted(body, key=lambda r: -int(r[ci['# Samples']] or 0))[:top_n]:

@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -cudart static"
-SRCS="api.cu conv_generic.cu conv_tc.cu elementwise.cu warp.cu ltam.cu evalpath.cu resblock_chain.cu"
+SRCS="api.cu conv_generic.cu conv_tc.cu elementwise.cu warp.cu ltam.cu evalpath.cu resblock_chain.cu tab_mix.cu"
 mkdir -p build
 OBJS=""
 PIDS=""

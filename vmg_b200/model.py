@@ -367,6 +367,18 @@ class VMG(nn.Module):
         o = _ops
         N, H, W, C = x.shape
         sm = blk.spatial_mixing
+        if self.channel_mixer == 'vanilla' and o.tab_mix_supported(x, C, sm.chunk_h, sm.chunk_w):
+            # fused mixing half (csrc/tab_mix.cu): LayerNorm, both Morph-FC token mixers, the channel mixer, the global
+            # mean, the 3-way mix, the gated projection and the residual in two passes over x
+            for lin, gamma in ((sm.mlp_h[0], sm.gamma_h), (sm.mlp_w[0], sm.gamma_w)):
+                o.decay_weights_(lin.weight.data, gamma)                 # function.py:765-768 / 778-781
+            pcs = (self._pc(sm.mlp_h[0], force=True), self._pc(sm.mlp_w[0], force=True), self._pc(sm.mlp_c[0]), self._pc(sm.proj))
+            acc = o.tab_mix(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, pcs, 0, B)
+            a = o.fixsum_finalize(acc, 1.0 / (T * H * W))                # function.py:791
+            a = o.linear(a, self._pc(sm.reweight.fc1, tc=False), act=o.ACT_GELU, use_tc=False)
+            a = o.softmax3(o.linear(a, self._pc(sm.reweight.fc2, tc=False), use_tc=False))
+            x = o.tab_mix(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, pcs, 1, B, a=a, m_scaling=self.m_scaling)
+            return self._tab_ffn(blk, x)
         xn = o.layernorm(x, blk.norm2.weight, blk.norm2.bias)
         branches = []
         for axis, (lin, gamma, chunk, Cp) in enumerate(((sm.mlp_h[0], sm.gamma_h, sm.chunk_h, sm.Ch),
@@ -397,6 +409,10 @@ class VMG(nn.Module):
         del h, w, c, branches
         x = o.linear(mix, self._pc(sm.proj), epi=o.EPI_GATE, res=x, aux=xn, res_scale=self.m_scaling)
         del mix, xn
+        return self._tab_ffn(blk, x)
+
+    def _tab_ffn(self, blk, x):
+        o = _ops
         xn = o.layernorm(x, blk.norm3.weight, blk.norm3.bias)
         cm = blk.channel_mixing
         u = o.conv2d(xn, self._pc(cm.fc1, groups=self.n_groups), act=o.ACT_GELU)

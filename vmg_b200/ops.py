@@ -359,6 +359,41 @@ def channel_sum(a, b, c, n_seg, groups, seg_rows, scale):
     return out
 
 
+def tab_mix_supported(x, C, chunk_h, chunk_w):
+    """Shapes the fused Morph-FC mixing kernel takes (csrc/tab_mix.cu)."""
+    return (x.dtype == torch.bfloat16 and x.is_contiguous() and chunk_h == 8 and chunk_w == 8 and C in (64, 112) and x.shape[-1] == C and
+            os.environ.get('VMGB_NO_TAB_MIX', '0') != '1')
+
+
+def tab_mix(x, ln_g, ln_b, eps, pcs, phase, B, acc=None, a=None, m_scaling=1.0):
+    """One phase of the fused mixing half of a TAB (include/vmgb.h vmgb_tab_mix).  pcs = PackedConv of (mlp_h, mlp_w, mlp_c, proj).
+    phase 0 returns the fixed-point accumulator [B, C]; phase 1 returns the new activation.  None if the shape is unsupported."""
+    require_device()
+    N, H, W, C = x.shape
+    ph, pw, pc, pp = pcs
+    assert all(q.wtc is not None and q.Kp == ph.Kp and q.Cin == C and q.Cout == C for q in pcs)
+    out = None
+    if phase == 0:
+        acc = torch.zeros((B, C), device=x.device, dtype=torch.int64)
+    else:
+        out = torch.empty_like(x)
+        assert a.dtype == torch.float32 and a.is_contiguous() and tuple(a.shape) == (B, 3, C)
+    rc = lib().vmgb_tab_mix(x.data_ptr(), ln_g.data_ptr(), ln_b.data_ptr(), float(eps), ph.wtc.data_ptr(), pw.wtc.data_ptr(), pc.wtc.data_ptr(),
+                            pp.wtc.data_ptr(), ph.Kp, _ptr(ph.bias), _ptr(pw.bias), _ptr(pc.bias), _ptr(pp.bias), phase, _ptr(acc), _ptr(a),
+                            _ptr(out), float(m_scaling), N, B, H, W, C, 8, _stream())
+    if rc == -2:
+        return None
+    _ck(rc, 'vmgb_tab_mix')
+    return acc if phase == 0 else out
+
+
+def fixsum_finalize(acc, scale):
+    require_device()
+    out = torch.empty(acc.shape, device=acc.device, dtype=torch.float32)
+    _ck(lib().vmgb_fixsum_finalize(acc.data_ptr(), out.data_ptr(), acc.numel(), float(scale), _stream()), 'vmgb_fixsum_finalize')
+    return out
+
+
 def softmax3(logits):
     require_device()
     B, C3 = logits.shape
