@@ -131,6 +131,21 @@ def run_rows(iters):
         print(json.dumps({'case': name, 'ms': round(ms, 4), 'GBps': round(nb / ms / 1e6, 1)}), flush=True)
 
 
+def run_tab(iters, frames=25):
+    """The fused Morph-FC mixing half (csrc/tab_mix.cu) at the level-0 shape: phase 0 (stats) and phase 1 (apply)."""
+    flush = torch.zeros(64 * 1024 * 1024, device=DEV)
+    N, H, W, C = frames, 184, 320, 112
+    x = torch.randn(N, H, W, C, device=DEV).bfloat16()
+    g, b = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    pcs = tuple(ops.pack_conv(torch.randn(C, C, device=DEV) * 0.1, torch.randn(C, device=DEV) * 0.1, 1, tc=True) for _ in range(4))
+    a = torch.full((1, 3, C), 1.0 / 3, device=DEV)
+    nbytes = x.numel() * 2
+    for name, fn, nb in (('tab_mix_phase0', lambda: ops.tab_mix(x, g, b, 1e-5, pcs, 0, 1), nbytes),
+                         ('tab_mix_phase1', lambda: ops.tab_mix(x, g, b, 1e-5, pcs, 1, 1, a=a), 2 * nbytes)):
+        ms = timeit(fn, iters, flush)
+        print(json.dumps({'case': name, 'frames': N, 'ms': round(ms, 4), 'GBps': round(nb / ms / 1e6, 1)}), flush=True)
+
+
 def run_chain(iters):
     """The 15-block residual chain of one trajectory step: ONE persistent kernel vs 30 per-layer launches."""
     flush = torch.zeros(64 * 1024 * 1024, device=DEV)
@@ -175,3 +190,7 @@ if __name__ == '__main__':
         run_rows(a.iters)
     if a.what in ('chain', 'all'):
         run_chain(a.iters)
+    if a.what in ('tab', 'all'):
+        run_tab(a.iters)
+    if a.what == 'tab_small':
+        run_tab(1, frames=4)

@@ -171,7 +171,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw
       break;
     case VMGB_ACT_GELU:
 #pragma unroll
-      for (int j = 0; j < 16; j += 2) { if (p.dbg & 16) gelu_erf_fast2(v[j], v[j + 1]); else gelu_tanh2(v[j], v[j + 1]); }
+#ifdef VMGB_GELU_ERF      // A/B build only: ONE GELU flavour in the chunk body (two doubled it past the instruction cache: fc1 +40 %)
+      for (int j = 0; j < 16; j += 2) gelu_erf_fast2(v[j], v[j + 1]);
+#else
+      for (int j = 0; j < 16; j += 2) gelu_tanh2(v[j], v[j + 1]);
+#endif
       break;
     case VMGB_ACT_SIGMOID:
 #pragma unroll

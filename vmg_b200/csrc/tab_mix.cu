@@ -77,11 +77,14 @@ tab_mix_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant_
   float* fl = reinterpret_cast<float*>(base_ptr + (misc - base) + 64);
   float* gam_s = fl;                  // [128]
   float* bet_s = fl + 128;            // [128]
-  float* bias_s = fl + 256;           // [4][128]
-  float* a_s = fl + 768;              // [3][128], pre-multiplied by 1/C
-  float* mu_s = fl + 1152;            // [128] per-pixel LayerNorm mean of the current tile
-  float* rstd_s = fl + 1280;          // [128]
-  float* part_s = reinterpret_cast<float*>(base_ptr + 3u * wbytes);     // phase 0 only: [16 warps][128], in the (unused) proj-weight slot
+  float* biasp_s = fl + 256;          // [128] projection bias
+  float* biasc_s = fl + 384;          // [128] channel-branch bias
+  float* ac_s = fl + 512;             // [128] a_c / C of the current batch sample
+  float* mu_s = fl + 640;             // [128] per-pixel LayerNorm mean of the current tile
+  float* rstd_s = fl + 768;           // [128]
+  float* biashw_s = fl + 896;         // [2][8 r'][16]: token-mixer biases, S columns per r' padded to 16 (one LDS.128 per 4)
+  float* ahw_s = fl + 1152;           // [2][8 g][20]: a_h / a_w / C per channel group, padded to 20 (conflict-free LDS.128)
+  float* part_s = reinterpret_cast<float*>(base_ptr + 3u * wbytes);     // phase 0 only: [16 warps][8 g][16], in the (unused) proj-weight slot
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -100,9 +103,15 @@ tab_mix_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant_
   for (int c = tid; c < 128; c += TM_THREADS) {
     gam_s[c] = c < C ? p.ln_g[c] : 0.f;
     bet_s[c] = c < C ? p.ln_b[c] : 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) bias_s[j * 128 + c] = (c < C && p.bias[j]) ? p.bias[j][c] : 0.f;
+    biasp_s[c] = (c < C && p.bias[3]) ? p.bias[3][c] : 0.f;
+    biasc_s[c] = (c < C && p.bias[2]) ? p.bias[2][c] : 0.f;
+    ac_s[c] = 0.f;
   }
+  for (int c = tid; c < 256; c += TM_THREADS) {
+    const int j = c >> 7, rp = (c >> 4) & 7, i = c & 15;
+    biashw_s[c] = (i < S && p.bias[j]) ? p.bias[j][rp * S + i] : 0.f;
+  }
+  for (int c = tid; c < 320; c += TM_THREADS) ahw_s[c] = 0.f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -167,9 +176,11 @@ tab_mix_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant_
         if (cur_b >= 0 && tid < C && fix_acc != 0) atomicAdd(p.acc + (long long)cur_b * C + tid, (unsigned long long)fix_acc);
         fix_acc = 0;
       } else {
-        for (int c = tid; c < 3 * 128; c += TM_THREADS) {
-          const int j = c >> 7, cc = c & 127;
-          a_s[c] = cc < C ? p.a[((long long)bsm * 3 + j) * C + cc] * inv_c : 0.f;
+        for (int c = tid; c < C; c += TM_THREADS) {
+          const int g = c / S, i = c - g * S;
+          ahw_s[g * 20 + i] = p.a[((long long)bsm * 3 + 0) * C + c] * inv_c;
+          ahw_s[160 + g * 20 + i] = p.a[((long long)bsm * 3 + 1) * C + c] * inv_c;
+          ac_s[c] = p.a[((long long)bsm * 3 + 2) * C + c] * inv_c;
         }
       }
       cur_b = bsm;
@@ -241,7 +252,10 @@ tab_mix_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant_
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * cpq);
     if (p.phase == 0) {
       // ================= phase 0: per-channel sums of the three branches over the valid pixels =================
-      float* my = part_s + warp * 128;
+      // Column sums by TRANSPOSE-REDUCTION: at every butterfly level a lane keeps one half of its values and sends the
+      // other half, so 32 columns over 32 lanes cost 31 shuffles (a plain xor-reduce per column: 160) -- the shuffles
+      // share the MIO pipe with the shared-memory traffic, which bounds this kernel.
+      float* my = part_s + warp * 128;                     // [8 g][16]
 #pragma unroll 1
       for (int j = 0; j < 2; ++j) {
         uint32_t u[32];
@@ -253,42 +267,70 @@ tab_mix_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant_
         for (int rr = 0; rr < 2; ++rr) {
           const int rp = 2 * cq + rr;                      // r' of these S columns
           const bool pv = j == 0 ? (rowv_h0 && h0 + rp < p.H) : (rowv_w0 && w0 + mb * 8 + rp < p.W);
+          float bq[16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(bq + 4 * k) = *reinterpret_cast<const float4*>(biashw_s + j * 128 + rp * 16 + 4 * k);
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             if (i < S) {
-              const float val = fmaxf(__uint_as_float(u[rr * S + i]) + bias_s[j * 128 + rp * S + i], 0.f);
+              const float val = fmaxf(__uint_as_float(u[rr * S + i]) + bq[i], 0.f);
               ps[i] += pv ? val : 0.f;
             }
         }
+        // lanes that share the channel group g = lane & 7 differ in lane bits 3 and 4: 16 -> 8 -> 4 values
+        {
+          const bool up = (lane & 16) != 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i < S) {
-            float t = ps[i];
-            t += __shfl_xor_sync(0xffffffffu, t, 8);
-            t += __shfl_xor_sync(0xffffffffu, t, 16);
-            if (lane < 8) { if (j == 0) my[lane * S + i] = t; else my[lane * S + i] += t; }
+          for (int i = 0; i < 8; ++i) {
+            const float send = up ? ps[i] : ps[i + 8], keep = up ? ps[i + 8] : ps[i];
+            ps[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
           }
+        }
+        {
+          const bool up = (lane & 8) != 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float send = up ? ps[i] : ps[i + 4], keep = up ? ps[i + 4] : ps[i];
+            ps[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+        }
+        // this lane now holds s' = 4 * (lane >> 3) .. + 3 of group g (s' >= S: zeros)
+        float4* dst = reinterpret_cast<float4*>(my + (lane & 7) * 16 + (lane >> 3) * 4);
+        if (j == 0) *dst = make_float4(ps[0], ps[1], ps[2], ps[3]);
+        else { const float4 o = *dst; *dst = make_float4(o.x + ps[0], o.y + ps[1], o.z + ps[2], o.w + ps[3]); }
         __syncwarp();
       }
       {
         uint32_t u[32];
         tmem_ld16_issue(tq + 256, u); tmem_ld16_issue(tq + 256 + 16, u + 16); tmem_ld_wait();
         const bool pv = h0 + (m >> 4) < p.H && w0 + (m & 15) < p.W;
+        float t[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < cpq) {
-            float t = pv ? fmaxf(__uint_as_float(u[i]) + bias_s[2 * 128 + cq * cpq + i], 0.f) : 0.f;
+        for (int k = 0; k < 8; ++k) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (4 * k < cpq) b4 = *reinterpret_cast<const float4*>(biasc_s + cq * cpq + 4 * k);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int sh = 16; sh >= 1; sh >>= 1) t += __shfl_xor_sync(0xffffffffu, t, sh);
-            if (lane == 0) my[cq * cpq + i] += t;
+          for (int e = 0; e < 4; ++e) t[4 * k + e] = (pv && 4 * k + e < cpq) ? fmaxf(__uint_as_float(u[4 * k + e]) + bb[e], 0.f) : 0.f;
+        }
+#pragma unroll
+        for (int half = 16; half >= 1; half >>= 1) {
+          const bool up = (lane & half) != 0;
+#pragma unroll
+          for (int i = 0; i < half; ++i) {
+            const float send = up ? t[i] : t[i + half], keep = up ? t[i + half] : t[i];
+            t[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
           }
+        }
+        // lane L holds the total of column L of this quarter
+        if (lane < cpq) { const int c = cq * cpq + lane, g = c / S; my[g * 16 + (c - g * S)] += t[0]; }
       }
       tc_fence_before();
       __syncthreads();
       if (tid < C) {
         float tot = 0.f;
 #pragma unroll
-        for (int w2 = 0; w2 < 16; ++w2) tot += part_s[w2 * 128 + tid];
+        for (int w2 = 0; w2 < 16; ++w2) tot += part_s[w2 * 128 + (tid / S) * 16 + (tid % S)];
         fix_acc += __float2ll_rn(tot * inv_c * 16777216.f);
       }
       __syncthreads();
@@ -299,16 +341,22 @@ tab_mix_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant_
     for (int j = 0; j < 2; ++j) {
       uint32_t u[32];
       tmem_ld16_issue(tq + j * 128, u); tmem_ld16_issue(tq + j * 128 + 16, u + 16); tmem_ld_wait();
+      float aq[16];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(aq + 4 * k) = *reinterpret_cast<const float4*>(ahw_s + j * 160 + mg * 20 + 4 * k);
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int rp = 2 * cq + rr;
+        float bq[16];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(bq + 4 * k) = *reinterpret_cast<const float4*>(biashw_s + j * 128 + rp * 16 + 4 * k);
         // H: pixel (row rp, column mb*8 + mw) ; W: pixel (row mw, column mb*8 + rp) -- channels mg*S + i
         const int prow = j == 0 ? rp * 16 + mb * 8 + mw : mw * 16 + mb * 8 + rp;
 #pragma unroll
         for (int i = 0; i < 16; i += 2)
           if (i < S) {
-            const float f0 = fmaxf(__uint_as_float(u[rr * S + i]) + bias_s[j * 128 + rp * S + i], 0.f) * a_s[j * 128 + mg * S + i];
-            const float f1 = fmaxf(__uint_as_float(u[rr * S + i + 1]) + bias_s[j * 128 + rp * S + i + 1], 0.f) * a_s[j * 128 + mg * S + i + 1];
+            const float f0 = fmaxf(__uint_as_float(u[rr * S + i]) + bq[i], 0.f) * aq[i];
+            const float f1 = fmaxf(__uint_as_float(u[rr * S + i + 1]) + bq[i + 1], 0.f) * aq[i + 1];
             sts32(t_s + j * tbytes + sw_word(prow, mg * S2 + (i >> 1)), bf2(f0, f1));
           }
       }
@@ -319,11 +367,11 @@ tab_mix_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 32; i += 4)
         if (i < cpq) {
-          float f[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) f[k] = fmaxf(__uint_as_float(u[i + k]) + bias_s[2 * 128 + cq * cpq + i + k], 0.f) * a_s[2 * 128 + cq * cpq + i + k];
+          const float4 b4 = *reinterpret_cast<const float4*>(biasc_s + cq * cpq + i), a4 = *reinterpret_cast<const float4*>(ac_s + cq * cpq + i);
+          const float f0 = fmaxf(__uint_as_float(u[i]) + b4.x, 0.f) * a4.x, f1 = fmaxf(__uint_as_float(u[i + 1]) + b4.y, 0.f) * a4.y;
+          const float f2 = fmaxf(__uint_as_float(u[i + 2]) + b4.z, 0.f) * a4.z, f3 = fmaxf(__uint_as_float(u[i + 3]) + b4.w, 0.f) * a4.w;
           const int word = (cq * cpq + i) >> 1;            // two words, 8-byte aligned (cpq % 4 == 0)
-          sts64(t_s + 2u * tbytes + sw_word(m, word), bf2(f[0], f[1]), bf2(f[2], f[3]));
+          sts64(t_s + 2u * tbytes + sw_word(m, word), bf2(f0, f1), bf2(f2, f3));
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -360,12 +408,14 @@ tab_mix_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant_
             const uint2 xr = *reinterpret_cast<const uint2*>(p.x + gp + i);
             const float xv[4] = {__uint_as_float(xr.x << 16), __uint_as_float(xr.x & 0xffff0000u), __uint_as_float(xr.y << 16),
                                  __uint_as_float(xr.y & 0xffff0000u)};
+            const float4 bp4 = *reinterpret_cast<const float4*>(biasp_s + cq * cpq + i), g4 = *reinterpret_cast<const float4*>(gam_s + cq * cpq + i),
+                         e4 = *reinterpret_cast<const float4*>(bet_s + cq * cpq + i);
+            const float bpv[4] = {bp4.x, bp4.y, bp4.z, bp4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w}, ev[4] = {e4.x, e4.y, e4.z, e4.w};
             float o[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int c = cq * cpq + i + k;
-              const float z = __uint_as_float(u[i + k]) + bias_s[3 * 128 + c];
-              const float xn = (xv[k] - mu) * rs * gam_s[c] + bet_s[c];
+              const float z = __uint_as_float(u[i + k]) + bpv[k];
+              const float xn = (xv[k] - mu) * rs * gv[k] + ev[k];
               float th;
               asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(z));
               o[k] = xv[k] + p.m_scaling * ((xn + z) * th);
@@ -449,7 +499,7 @@ extern "C" int vmgb_tab_mix(const void* x, const float* ln_g, const float* ln_b,
   p.n_tiles = (long long)n_img * p.tiles_h * p.tiles_w;
   p.eps = eps; p.m_scaling = m_scaling;
   const int wbytes = p.nkb * C * 128, tbytes = p.nkb * TM_TILE_KB;
-  const int smem = 1024 + 4 * wbytes + 3 * tbytes + 64 + 1408 * 4 + 64;
+  const int smem = 1024 + 4 * wbytes + 3 * tbytes + 64 + 1472 * 4 + 64;
   if (smem > g_smem_t) return VMGB_EUNSUPPORTED;
   CUtensorMap mW[4];
   const void* ws[4] = {w_h, w_w, w_c, phase ? w_p : w_c};
