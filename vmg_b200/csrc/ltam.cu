@@ -9,6 +9,25 @@
 
 namespace vmgb {
 
+// packed FP32x2 (Blackwell FFMA2: one issue slot per TWO fp32 lanes, the same rounding as scalar fma.rn)
+__device__ __forceinline__ unsigned long long lt_pack(float a, float b) {
+  return (unsigned long long)__float_as_uint(a) | ((unsigned long long)__float_as_uint(b) << 32);
+}
+__device__ __forceinline__ unsigned long long lt_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long lt_mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// a 32-bit word holding two bf16 -> the packed pair (element 2k, element 2k+1) as fp32
+__device__ __forceinline__ unsigned long long lt_unpack(uint32_t w) {
+  return (unsigned long long)(w << 16) | ((unsigned long long)(w & 0xffff0000u) << 32);
+}
+
 template <int D4>
 __global__ void __launch_bounds__(128) ltam_wins_kernel(const void* q, const void* keys, const void* vals, int dt, long long kv_stride,
                                                         const float* __restrict__ loc, int loc_pitch, const float* __restrict__ rel,
@@ -121,12 +140,14 @@ __global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16
     src_s[idx] = (sx >= 0 && sx < w && sy >= 0 && sy < h) ? (int)(((long long)i2 * h + sy) * w + sx) : -1;
   }
 
-  float qv[D], acc[D];
+  // queries and accumulators as packed fp32 pairs (element 2k, 2k+1)
+  unsigned long long qv2[D / 2], acc2[D / 2];
 #pragma unroll
   for (int i = 0; i < D4; ++i) {
     const float4 v = ld4(q, VMGB_BF16, qpix * C + head * D + i * 4);
-    qv[4 * i] = v.x * scale; qv[4 * i + 1] = v.y * scale; qv[4 * i + 2] = v.z * scale; qv[4 * i + 3] = v.w * scale;
-    acc[4 * i] = acc[4 * i + 1] = acc[4 * i + 2] = acc[4 * i + 3] = 0.f;
+    qv2[2 * i] = lt_pack(v.x * scale, v.y * scale);
+    qv2[2 * i + 1] = lt_pack(v.z * scale, v.w * scale);
+    acc2[2 * i] = 0ull; acc2[2 * i + 1] = 0ull;
   }
   const float dh = decay[head];
   float relq[4];
@@ -171,29 +192,41 @@ __global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
     pe *= dh;
-    const uint8_t* base = sm + buf * (2 * 32 * ROWB);
+    const uint32_t rowk = (uint32_t)__cvta_generic_to_shared(sm + buf * (2 * 32 * ROWB) + (wl * 4) * ROWB + head * D * 2);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const __nv_bfloat16* kr = reinterpret_cast<const __nv_bfloat16*>(base + (wl * 4 + j) * ROWB) + head * D;
-      const __nv_bfloat16* vr = kr + 32 * C;
-      float dot = 0.f;
+      const uint32_t kr = rowk + j * ROWB, vr = kr + 32 * ROWB;
+      // dot product on packed pairs: 8-byte shared loads (4 bf16), two fused multiply-adds per load
+      unsigned long long d2 = 0ull;
 #pragma unroll
       for (int i = 0; i < D4; ++i) {
-        const float4 kv = ld4(kr, VMGB_BF16, i * 4);
-        dot += kv.x * qv[4 * i] + kv.y * qv[4 * i + 1] + kv.z * qv[4 * i + 2] + kv.w * qv[4 * i + 3];
+        uint32_t w0, w1;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(kr + i * 8));
+        d2 = lt_fma2(lt_unpack(w0), qv2[2 * i], d2);
+        d2 = lt_fma2(lt_unpack(w1), qv2[2 * i + 1], d2);
       }
-      const float logit = dot + pe * relq[j];
-      const float mn = fmaxf(m, logit);
-      const float corr = __expf(m - mn), pw = __expf(logit - mn);
-      l = l * corr + pw;
-      m = mn;
+      const float logit = __uint_as_float((uint32_t)d2) + __uint_as_float((uint32_t)(d2 >> 32)) + pe * relq[j];
+      // online softmax with a LAZY reference point: keys and queries are L2-normalised over the full channel vector, so the
+      // logits of one pixel span a few units at most; the running reference m is only moved (and the accumulators rescaled)
+      // when a logit exceeds it by more than 16 -- in practice once, at the first key (m = -inf).  exp(logit - m) / sum is
+      // the same softmax as with the true maximum.
+      if (logit > m + 16.f) {
+        const float corr = __expf(m - logit);
+        const unsigned long long c2 = lt_pack(corr, corr);
+        l *= corr;
+#pragma unroll
+        for (int i = 0; i < D / 2; ++i) acc2[i] = lt_mul2(acc2[i], c2);
+        m = logit;
+      }
+      const float pw = __expf(logit - m);
+      l += pw;
+      const unsigned long long p2 = lt_pack(pw, pw);
 #pragma unroll
       for (int i = 0; i < D4; ++i) {
-        const float4 vv = ld4(vr, VMGB_BF16, i * 4);
-        acc[4 * i] = acc[4 * i] * corr + pw * vv.x;
-        acc[4 * i + 1] = acc[4 * i + 1] * corr + pw * vv.y;
-        acc[4 * i + 2] = acc[4 * i + 2] * corr + pw * vv.z;
-        acc[4 * i + 3] = acc[4 * i + 3] * corr + pw * vv.w;
+        uint32_t w0, w1;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(vr + i * 8));
+        acc2[2 * i] = lt_fma2(lt_unpack(w0), p2, acc2[2 * i]);
+        acc2[2 * i + 1] = lt_fma2(lt_unpack(w1), p2, acc2[2 * i + 1]);
       }
     }
     if (++buf == NST) buf = 0;
@@ -203,7 +236,8 @@ __global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16
 #pragma unroll
   for (int i = 0; i < D4; ++i)
     st4(out, out_dt, qpix * C + head * D + i * 4,
-        make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv));
+        make_float4(__uint_as_float((uint32_t)acc2[2 * i]) * inv, __uint_as_float((uint32_t)(acc2[2 * i] >> 32)) * inv,
+                    __uint_as_float((uint32_t)acc2[2 * i + 1]) * inv, __uint_as_float((uint32_t)(acc2[2 * i + 1] >> 32)) * inv));
 }
 
 }  // namespace vmgb

@@ -50,6 +50,11 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st
 __device__ __forceinline__ void sts64(uint32_t a, uint32_t v0, uint32_t v1) {
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v0), "r"(v1) : "memory");
 }
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -392,36 +397,66 @@ tab_mix_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant_
       }
       __syncwarp();
     }
+    // the gate needs x again at (pixel = accumulator row, 28 channels): a row-per-lane global access touches 32 lines per
+    // instruction (the L1 tag stage was the phase-1 bottleneck), so the x tile comes in with coalesced 16-byte loads
+    // while the projection runs, is staged in the (now dead) operand buffers with a conflict-free pitch, and the
+    // result leaves the same way
+    constexpr int CPP = C / 8, NCH = 128 * CPP, PIT = C * 2 + 8;      // 16-byte chunks per pixel / per tile; staging pitch
+    constexpr uint32_t OS_OFF = (uint32_t)((128 * PIT + 1023) / 1024 * 1024);      // output staging behind the x staging (both inside the 3 operand tiles)
+    static_assert(2 * OS_OFF <= 3 * tbytes, "staging does not fit");
+    uint4 xr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int id = tid + TM_THREADS * k, pm = id / CPP, c16 = id - pm * CPP, r = pm >> 4, col = pm & 15;
+      xr[k] = make_uint4(0, 0, 0, 0);
+      if (id < NCH && h0 + r < p.H && w0 + col < p.W)
+        xr[k] = __ldg(reinterpret_cast<const uint4*>(p.x + (((long long)img * p.H + h0 + r) * p.W + w0 + col) * C + c16 * 8));
+    }
     mbar_wait(bar2, ph2); ph2 ^= 1;
     tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int id = tid + TM_THREADS * k, pm = id / CPP, c16 = id - pm * CPP;
+      if (id < NCH) {
+        sts64(t_s + (uint32_t)(pm * PIT + c16 * 16), xr[k].x, xr[k].y);
+        sts64(t_s + (uint32_t)(pm * PIT + c16 * 16 + 8), xr[k].z, xr[k].w);
+      }
+    }
+    __syncthreads();
     // ================= gate + residual: out = x + m * (LN2(x) + z) * tanh(z) =================
     {
       uint32_t u[32];
       tmem_ld16_issue(tq + 384, u); tmem_ld16_issue(tq + 384 + 16, u + 16); tmem_ld_wait();
-      const int r = m >> 4, col = m & 15;
-      if (h0 + r < p.H && w0 + col < p.W) {
-        const long long gp = (((long long)img * p.H + h0 + r) * p.W + w0 + col) * C + cq * cpq;
-        const float mu = mu_s[m], rs = rstd_s[m];
+      const float mu = mu_s[m], rs = rstd_s[m];
+      const uint32_t xs = t_s + (uint32_t)(m * PIT + cq * cpq * 2), os = xs + OS_OFF;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          if (i < cpq) {
-            const uint2 xr = *reinterpret_cast<const uint2*>(p.x + gp + i);
-            const float xv[4] = {__uint_as_float(xr.x << 16), __uint_as_float(xr.x & 0xffff0000u), __uint_as_float(xr.y << 16),
-                                 __uint_as_float(xr.y & 0xffff0000u)};
-            const float4 bp4 = *reinterpret_cast<const float4*>(biasp_s + cq * cpq + i), g4 = *reinterpret_cast<const float4*>(gam_s + cq * cpq + i),
-                         e4 = *reinterpret_cast<const float4*>(bet_s + cq * cpq + i);
-            const float bpv[4] = {bp4.x, bp4.y, bp4.z, bp4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w}, ev[4] = {e4.x, e4.y, e4.z, e4.w};
-            float o[4];
+      for (int i = 0; i < 32; i += 4)
+        if (i < cpq) {
+          const uint2 xw = lds64(xs + i * 2);
+          const float xv[4] = {__uint_as_float(xw.x << 16), __uint_as_float(xw.x & 0xffff0000u), __uint_as_float(xw.y << 16),
+                               __uint_as_float(xw.y & 0xffff0000u)};
+          const float4 bp4 = *reinterpret_cast<const float4*>(biasp_s + cq * cpq + i), g4 = *reinterpret_cast<const float4*>(gam_s + cq * cpq + i),
+                       e4 = *reinterpret_cast<const float4*>(bet_s + cq * cpq + i);
+          const float bpv[4] = {bp4.x, bp4.y, bp4.z, bp4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w}, ev[4] = {e4.x, e4.y, e4.z, e4.w};
+          float o[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float z = __uint_as_float(u[i + k]) + bpv[k];
-              const float xn = (xv[k] - mu) * rs * gv[k] + ev[k];
-              float th;
-              asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(z));
-              o[k] = xv[k] + p.m_scaling * ((xn + z) * th);
-            }
-            *reinterpret_cast<uint2*>(p.out + gp + i) = make_uint2(bf2(o[0], o[1]), bf2(o[2], o[3]));
+          for (int k = 0; k < 4; ++k) {
+            const float z = __uint_as_float(u[i + k]) + bpv[k];
+            const float xn = (xv[k] - mu) * rs * gv[k] + ev[k];
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(z));
+            o[k] = xv[k] + p.m_scaling * ((xn + z) * th);
           }
+          sts64(os + i * 2, bf2(o[0], o[1]), bf2(o[2], o[3]));
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int id = tid + TM_THREADS * k, pm = id / CPP, c16 = id - pm * CPP, r = pm >> 4, col = pm & 15;
+      if (id < NCH && h0 + r < p.H && w0 + col < p.W) {
+        const uint2 lo = lds64(t_s + OS_OFF + (uint32_t)(pm * PIT + c16 * 16)), hi = lds64(t_s + OS_OFF + (uint32_t)(pm * PIT + c16 * 16 + 8));
+        *reinterpret_cast<uint4*>(p.out + (((long long)img * p.H + h0 + r) * p.W + w0 + col) * C + c16 * 8) = make_uint4(lo.x, lo.y, hi.x, hi.y);
       }
     }
     tc_fence_before();
