@@ -182,6 +182,9 @@ int vmgb_unpair_sweeps(const void* paired, void* back, void* fwd, int T, long lo
 
 /* elementwise out = a + b */
 int vmgb_add(const void* a, const void* b, int dt, void* out, int out_dt, long long n, void* stream);
+/* out [n_img,H,W,C] = (a + b)[:, :H, :W, :] for bf16 channels-last a, b [n_img,Hp,Wp,C], C % 8 == 0: the last skip connection
+ * (vmg.py:547 / :581) and the crop back to the unpadded size (vmg.py:619) in one pass.  VMGB_EUNSUPPORTED for other layouts. */
+int vmgb_add_crop(const void* a, const void* b, void* out, int n_img, int Hp, int Wp, int H, int W, int C, void* stream);
 
 /* W *= gamma in place, fp32 (function.py:765-768,778-781) */
 int vmgb_decay_weights(float* w, const float* gamma, long long n, void* stream);

@@ -228,6 +228,51 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16
 }
 
 // ---------------------------------------------------------------------------------------------
+// Register-resident variant for Cin = 3 (the RGB input conv: 3 -> C over every LQ pixel, 5.9 M pixels per headline clip).
+// The shared-memory version below reads 54 weight vectors per 8 outputs through the MIO pipe (14 different addresses per
+// warp instruction) and measured 5.0 ms = 0.28 TB/s; here a thread keeps the 27 x 4 weights of FOUR output channels in
+// registers for the whole launch and walks the pixels grid-stride, the 27 inputs of a pixel are L1 broadcasts shared by
+// the C/4 threads of that pixel, and those threads write the pixel's channel run as consecutive 8-byte pieces.
+__global__ void __launch_bounds__(256, 1) conv3x3_rgb_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int out_pitch,
+                                                             int n_img, int H, int W, int Cout, int act, float alpha, float out_scale,
+                                                             long long n_pix) {
+  const int nq = Cout >> 2;                      // channel quads per pixel
+  const int ppb = blockDim.x / nq;               // pixels per block iteration
+  const int slot = threadIdx.x / nq, cq = threadIdx.x - slot * nq;
+  if (slot >= ppb) return;
+  const int co = cq * 4;
+  float wr[27][4];                               // packed weights are [tap][ci][co]
+#pragma unroll
+  for (int k = 0; k < 27; ++k) {
+    const float4 t = *reinterpret_cast<const float4*>(w + k * Cout + co);
+    wr[k][0] = t.x; wr[k][1] = t.y; wr[k][2] = t.z; wr[k][3] = t.w;
+  }
+  float b4[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b4[j] = bias ? bias[co + j] : 0.f;
+  for (long long pix = (long long)blockIdx.x * ppb + slot; pix < n_pix; pix += (long long)gridDim.x * ppb) {
+    const int ww = (int)(pix % W); const long long t = pix / W; const int hh = (int)(t % H); const int img = (int)(t / H);
+    float acc[4] = {b4[0], b4[1], b4[2], b4[3]};
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int y = hh + tap / 3 - 1, xx = ww + tap % 3 - 1;
+      const bool in = y >= 0 && y < H && xx >= 0 && xx < W;
+      const float* xp = x + (((long long)img * H + (in ? y : hh)) * W + (in ? xx : ww)) * x_pitch;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float xv = in ? __ldg(xp + ci) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(xv, wr[tap * 3 + ci][j], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = apply_act(acc[j], act, alpha) * out_scale;
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
+    *reinterpret_cast<uint2*>(out + pix * out_pitch + co) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  }
+}
+
 // 3x3 convolution with a tiny input (Cin <= 4, fp32 NHWC, one group, plain store): the network's first conv
 // (input_proj 3 -> C, vmg.py:378-386).  K = 27 is far too small for the implicit-GEMM tiles above (6.5 ms for the
 // headline clip, 5 TFLOP/s); here a thread owns 8 output channels of one pixel, the packed weights [tap][ci][co] and
@@ -309,6 +354,17 @@ extern "C" int vmgb_conv2d_nhwc(const void* x, const void* x1, const void* x2, i
       (Cout & 7) == 0 && Cout <= 256 && (out_pitch & 7) == 0 && !(reinterpret_cast<uintptr_t>(out) & 15) &&
       (long long)n_img * H * W >= 4096) {
     const long long n_pix = (long long)n_img * H * W;
+    if (Cin == 3 && out_dt == VMGB_BF16 && (Cout & 3) == 0 && Cout <= 1024 && (out_pitch & 3) == 0 && !(reinterpret_cast<uintptr_t>(out) & 7) &&
+        !(reinterpret_cast<uintptr_t>(w) & 15)) {
+      const int ppb4 = 256 / (Cout >> 2);
+      if (ppb4 >= 1) {
+        const long long wanted4 = (n_pix + ppb4 - 1) / ppb4;
+        const unsigned grid4 = (unsigned)(wanted4 < 148 * 2 ? wanted4 : 148 * 2);   // ~170 registers: one block per SM resident, two queued
+        conv3x3_rgb_kernel<<<grid4, 256, 0, as_stream(stream)>>>((const float*)x, x_pitch, (const float*)w, (const float*)bias, (__nv_bfloat16*)out,
+                                                                 out_pitch, n_img, H, W, Cout, act, act_alpha, out_scale, n_pix);
+        return check_launch();
+      }
+    }
     const int ppb = 256 / (Cout >> 3);
     const long long wanted = (n_pix + ppb - 1) / ppb;
     const unsigned grid = (unsigned)(wanted < 148 * 8 ? wanted : 148 * 8);

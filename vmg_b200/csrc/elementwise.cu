@@ -595,6 +595,28 @@ __global__ void add_kernel(const void* a, const void* b, int dt, void* out, int 
     stf(out, out_dt, i, ldf(a, dt, i) + ldf(b, dt, i));
 }
 
+// out[n, h < H, w < W, :] = a + b over [n, Hp, Wp, C] bf16 operands (the last skip connection of the U-Net, vmg.py:547, and the
+// crop back to the input size, vmg.py:619, in one pass; 16 bytes per thread)
+__global__ void __launch_bounds__(256) add_crop_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
+                                                            int Hp, int Wp, int H, int W, int C8, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8); long long t = i / C8;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H); const long long n = t / H;
+    const long long src = ((n * Hp + h) * Wp + w) * C8 + c;
+    const uint4 va = __ldg(a + src), vb = __ldg(b + src);
+    const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 hsum = __floats2bfloat162_rn(__uint_as_float(wa[k] << 16) + __uint_as_float(wb[k] << 16),
+                                                        __uint_as_float(wa[k] & 0xffff0000u) + __uint_as_float(wb[k] & 0xffff0000u));
+      o[k] = *reinterpret_cast<const uint32_t*>(&hsum);
+    }
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 __global__ void decay_kernel(float* __restrict__ w, const float* __restrict__ g, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     w[i] = w[i] * g[i];
@@ -880,6 +902,14 @@ extern "C" int vmgb_unpair_sweeps(const void* paired, void* back, void* fwd, int
 extern "C" int vmgb_add(const void* a, const void* b, int dt, void* out, int out_dt, long long n, void* stream) {
   if (!a || !b || !out || !dt_ok(dt) || !dt_ok(out_dt) || n <= 0) return VMGB_EINVAL;
   add_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(a, b, dt, out, out_dt, n);
+  return check_launch();
+}
+
+extern "C" int vmgb_add_crop(const void* a, const void* b, void* out, int n_img, int Hp, int Wp, int H, int W, int C, void* stream) {
+  if (!a || !b || !out || n_img < 1 || H < 1 || W < 1 || H > Hp || W > Wp || C < 8) return VMGB_EINVAL;
+  if ((C & 7) || ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15)) return VMGB_EUNSUPPORTED;
+  const long long total = (long long)n_img * H * W * (C / 8);
+  add_crop_bf16_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>((const uint4*)a, (const uint4*)b, (uint4*)out, Hp, Wp, H, W, C / 8, total);
   return check_launch();
 }
 

@@ -581,7 +581,7 @@ class VMG(nn.Module):
             x5 = self._stage(D[0], self._resample(self.upsample[0], x4, x2_4), B, T, None)
             x6 = self._stage(D[1], self._resample(self.upsample[1], x5, x3), B, T, None)
             x7 = self._stage(D[2], self._resample(self.upsample[2], x6, x2), B, T, flows)
-            y = o.add(x7, x1)
+            y = o.add_crop(x7, x1, H, W)                                  # skip connection + the crop of vmg.py:619 in one pass
         else:                                                             # vmg.py:569-582
             x1 = self._stage(E[0], x0, B, T, flows)
             x2 = self._stage(E[1], self._resample(self.downsample[0], x1), B, T, None)
@@ -589,7 +589,7 @@ class VMG(nn.Module):
             y = o.add(x3, x1)
         if self.local_fuse:                                               # vmg.py:616-617
             y = o.conv2d(y, self._pc(self.local_cnn), epi=o.EPI_RESADD, res=x0)
-        if Hp != H or Wp != W:
+        if y.shape[1] != H or y.shape[2] != W:
             y = y[:, :H, :W, :].contiguous()                              # vmg.py:619
         out = torch.empty((B, T, 3, 4 * H, 4 * W), device=x.device, dtype=torch.float32)
         C = y.shape[-1]

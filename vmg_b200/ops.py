@@ -452,6 +452,22 @@ def add(a, b):
     return out
 
 
+def add_crop(a, b, H, W):
+    """(a + b)[:, :H, :W, :] for [N,Hp,Wp,C] tensors in one pass (bf16, C % 8 == 0), else add + slice."""
+    require_device()
+    N, Hp, Wp, C = a.shape
+    assert a.shape == b.shape and a.dtype == b.dtype and a.is_contiguous() and b.is_contiguous()
+    if a.dtype == torch.bfloat16 and C % 8 == 0:
+        out = torch.empty((N, H, W, C), device=a.device, dtype=a.dtype)
+        rc = lib().vmgb_add_crop(a.data_ptr(), b.data_ptr(), out.data_ptr(), N, Hp, Wp, H, W, C, _stream())
+        if rc == 0:
+            return out
+        if rc != -2:
+            _ck(rc, 'vmgb_add_crop')
+    y = add(a, b)
+    return y if (Hp == H and Wp == W) else y[:, :H, :W, :].contiguous()
+
+
 def decay_weights_(w, gamma):
     require_device()
     assert w.dtype == torch.float32 and gamma.dtype == torch.float32 and w.is_contiguous() and gamma.is_contiguous()
