@@ -41,8 +41,26 @@ def main():
     loc2 = torch.empty_like(loc)
     flow = rnd(2, H, W, 2) * 3
     rel, dec = torch.zeros(4, 4, 4, device=DEV), torch.full((4,), 0.97, device=DEV)
+    tab_pcs = tuple(pk(112, 112, 1) for _ in range(4))
+    tab_a = torch.full((1, 3, C), 1.0 / 3, device=DEV)
+    rgb = rnd(N, H, W, 3)
+    rgb_pc = ops.pack_conv(rnd(112, 3, 3, 3) * 0.1, rnd(112) * 0.1, 1, tc=False)
+    x1 = rnd(4 * N, 92, 160, 224).bfloat16()                 # level-1 activations (chunk 16, C = 224): the unfused TAB glue
+    lin1, proj1 = pk(224, 224, 1), pk(224, 224, 1)
+    A1 = ops.morph_gather(x1, 16, 0)
+    a31 = torch.rand(1, 3, 224, device=DEV)
     torch.cuda.synchronize()
     cases = {
+        'tab_mix_phase0': lambda: ops.tab_mix(x, gam, bet, 1e-5, tab_pcs, 0, 1),
+        'tab_mix_phase1': lambda: ops.tab_mix(x, gam, bet, 1e-5, tab_pcs, 1, 1, a=tab_a),
+        'rgb_input_conv': lambda: ops.conv2d(rgb, rgb_pc, act=ops.ACT_LRELU, alpha=0.01, out_dtype=torch.bfloat16, use_tc=False),
+        'l1_linear_relu_224': lambda: ops.linear(x1, lin1, act=ops.ACT_RELU, out_scale=1.0 / 224),
+        'l1_proj_gate_224': lambda: ops.linear(x1, proj1, epi=ops.EPI_GATE, res=x1, aux=x1),
+        'l1_morph_gather_16': lambda: ops.morph_gather(x1, 16, 1),
+        'l1_morph_scatter_16': lambda: ops.morph_scatter(A1, 4 * N, 92, 160, 224, 16, 0),
+        'l1_channel_sum': lambda: ops.channel_sum(x1, x1, x1, 4 * N, 1, 92 * 160, 1.0),
+        'l1_mix3': lambda: ops.mix3(x1, x1, x1, a31, 4 * N, 1, 92 * 160),
+        'l1_layernorm_224': lambda: ops.layernorm(x1, torch.ones(224, device=DEV), torch.zeros(224, device=DEV)),
         'ffn_fc1': lambda: ops.conv2d(x, fc1, act=ops.ACT_GELU),
         'ffn_fc2': lambda: ops.linear(hidden, fc2, epi=ops.EPI_RESADD, res=x),
         'linear_relu': lambda: ops.linear(x, lin, act=ops.ACT_RELU, out_scale=1.0 / C),
