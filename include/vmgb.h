@@ -218,10 +218,15 @@ int vmgb_l2norm(const void* x, int x_dt, int x_pitch, void* out, int out_dt, lon
  * vals   [Kcap][n,h,w,C]      key-frame propagated features
  * loc    fp32 [n,h,w,loc_pitch] tracked (x,y) per key-frame, channels 2k,2k+1
  * rel    fp32 [heads][4][4], decay fp32 [heads]
- * out    [n,h,w,C]  attention output BEFORE the proj Linear (proj + anchor add = conv2d RESADD) */
+ * out    [n,h,w,C]  attention output BEFORE the proj Linear (proj + anchor add = conv2d RESADD), or -- with
+ *        out_bias / anchor given -- out = attention(vals) + out_bias[c] + anchor[pixel][c]: the caller stores the values
+ *        ALREADY PROJECTED (vals_k = proj.weight . sparse_k, one launch per key frame instead of one per step; exact
+ *        in real arithmetic because proj is linear and the softmax weights sum to 1: trajectory.py:791-795), out_bias =
+ *        proj.bias (fp32 [C], 16-byte aligned) and anchor = the warped propagated feature (dtype out_dt, pitch C). */
 int vmgb_ltam_wins(const void* q, const void* keys, const void* vals, int dt, long long kv_stride,
                    const float* loc, int loc_pitch, const float* rel, const float* decay,
-                   void* out, int out_dt, int n, int h, int w, int C, int heads, int K, void* stream);
+                   void* out, int out_dt, int n, int h, int w, int C, int heads, int K,
+                   const float* out_bias, const void* anchor, void* stream);
 
 /* ---- resampling (layers.py:777-798): pixel-(un)shuffle gather + LayerNorm fused; Linear follows.
  * down: x[BT,H,W,C] -> out[BT,H/2,W/2,4C] feature (neiw,neih,c);  up: x[BT,H,W,C] -> out[BT,2H,2W,C/4].

@@ -239,7 +239,7 @@ def test_flow_warps(dtype, tol):
     close(ops.flow_smooth(flow.to(DEV), 4), emu.flow_smooth(flow, 4), 1e-5)
 
 
-@pytest.mark.parametrize('C,dtype,tol', [(112, torch.float32, 2e-5), (144, torch.float32, 2e-5), (144, torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize('C,dtype,tol', [(112, torch.float32, 2e-5), (144, torch.float32, 2e-5), (144, torch.bfloat16, 2e-2), (112, torch.bfloat16, 2e-2)])
 def test_ltam_wins(C, dtype, tol):
     n, h, w, heads, T, stride = 2, 12, 16, 4, 9, 3
     feats = rnd(T, n, h, w, C, seed=1).to(dtype)
@@ -257,6 +257,11 @@ def test_ltam_wins(C, dtype, tol):
         ref = emu.ltam_wins(q, keys[first], feats[first], kstep * fe, K, loc, rel, decay, heads)
         out = ops.ltam_wins(dk[4], dk[first], dv[first], kstep * fe, K, loc.to(DEV), rel.to(DEV), decay.to(DEV), heads)
         close(out, ref, tol)
+        # values stored already projected: the kernel adds the projection bias and the warped anchor itself
+        bias, anchor = rnd(C, seed=11, scale=0.5), rnd(n, h, w, C, seed=12).to(dtype)
+        out2 = ops.ltam_wins(dk[4], dk[first], dv[first], kstep * fe, K, loc.to(DEV), rel.to(DEV), decay.to(DEV), heads,
+                             out_bias=bias.to(DEV), anchor=anchor.to(DEV))
+        close(out2, ref + bias + anchor.float(), 2 * tol)
 
 
 def test_spynet_helpers_and_io():

@@ -236,11 +236,13 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16
 __global__ void __launch_bounds__(256, 1) conv3x3_rgb_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ w,
                                                              const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int out_pitch,
                                                              int n_img, int H, int W, int Cout, int act, float alpha, float out_scale,
-                                                             long long n_pix) {
-  const int nq = Cout >> 2;                      // channel quads per pixel
-  const int ppb = blockDim.x / nq;               // pixels per block iteration
+                                                             long long n_quads) {
+  // a thread = 4 output channels x 4 horizontally adjacent pixels (W % 4 == 0): 16 independent accumulators, the 3 x 6 x 3
+  // input patch is loaded once per kernel row and shared by the four pixels
+  const int nq = Cout >> 2;                      // channel quads per pixel group
+  const int gpb = blockDim.x / nq;               // pixel groups per block iteration
   const int slot = threadIdx.x / nq, cq = threadIdx.x - slot * nq;
-  if (slot >= ppb) return;
+  if (slot >= gpb) return;
   const int co = cq * 4;
   float wr[27][4];                               // packed weights are [tap][ci][co]
 #pragma unroll
@@ -251,25 +253,45 @@ __global__ void __launch_bounds__(256, 1) conv3x3_rgb_kernel(const float* __rest
   float b4[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) b4[j] = bias ? bias[co + j] : 0.f;
-  for (long long pix = (long long)blockIdx.x * ppb + slot; pix < n_pix; pix += (long long)gridDim.x * ppb) {
-    const int ww = (int)(pix % W); const long long t = pix / W; const int hh = (int)(t % H); const int img = (int)(t / H);
-    float acc[4] = {b4[0], b4[1], b4[2], b4[3]};
+  const int wq = W >> 2;
+  for (long long q = (long long)blockIdx.x * gpb + slot; q < n_quads; q += (long long)gridDim.x * gpb) {
+    const int w0 = (int)(q % wq) * 4; const long long t = q / wq; const int hh = (int)(t % H); const int img = (int)(t / H);
+    float acc[4][4];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int y = hh + tap / 3 - 1, xx = ww + tap % 3 - 1;
-      const bool in = y >= 0 && y < H && xx >= 0 && xx < W;
-      const float* xp = x + (((long long)img * H + (in ? y : hh)) * W + (in ? xx : ww)) * x_pitch;
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        const float xv = in ? __ldg(xp + ci) : 0.f;
+      for (int j = 0; j < 4; ++j) acc[p][j] = b4[j];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = fmaf(xv, wr[tap * 3 + ci][j], acc[j]);
+    for (int r = 0; r < 3; ++r) {
+      const int y = hh + r - 1;
+      const bool yin = y >= 0 && y < H;
+      const float* row = x + ((long long)img * H + (yin ? y : hh)) * W * x_pitch;
+      float in[6][3];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const int xx = w0 + c - 1;
+        const bool ok = yin && xx >= 0 && xx < W;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) in[c][ci] = ok ? __ldg(row + (long long)xx * x_pitch + ci) : 0.f;
       }
-    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = apply_act(acc[j], act, alpha) * out_scale;
-    const __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
-    *reinterpret_cast<uint2*>(out + pix * out_pitch + co) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      for (int sx = 0; sx < 3; ++sx)
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[p][j] = fmaf(in[p + sx][ci], wr[(r * 3 + sx) * 3 + ci][j], acc[p][j]);
+    }
+    const long long pix0 = ((long long)img * H + hh) * W + w0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = apply_act(acc[p][j], act, alpha) * out_scale;
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+      *reinterpret_cast<uint2*>(out + (pix0 + p) * out_pitch + co) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    }
   }
 }
 
@@ -354,14 +376,15 @@ extern "C" int vmgb_conv2d_nhwc(const void* x, const void* x1, const void* x2, i
       (Cout & 7) == 0 && Cout <= 256 && (out_pitch & 7) == 0 && !(reinterpret_cast<uintptr_t>(out) & 15) &&
       (long long)n_img * H * W >= 4096) {
     const long long n_pix = (long long)n_img * H * W;
-    if (Cin == 3 && out_dt == VMGB_BF16 && (Cout & 3) == 0 && Cout <= 1024 && (out_pitch & 3) == 0 && !(reinterpret_cast<uintptr_t>(out) & 7) &&
+    if (Cin == 3 && (W & 3) == 0 && out_dt == VMGB_BF16 && (Cout & 3) == 0 && Cout <= 1024 && (out_pitch & 3) == 0 && !(reinterpret_cast<uintptr_t>(out) & 7) &&
         !(reinterpret_cast<uintptr_t>(w) & 15)) {
       const int ppb4 = 256 / (Cout >> 2);
       if (ppb4 >= 1) {
-        const long long wanted4 = (n_pix + ppb4 - 1) / ppb4;
+        const long long n_quads = n_pix / 4;
+        const long long wanted4 = (n_quads + ppb4 - 1) / ppb4;
         const unsigned grid4 = (unsigned)(wanted4 < 148 * 2 ? wanted4 : 148 * 2);   // ~170 registers: one block per SM resident, two queued
         conv3x3_rgb_kernel<<<grid4, 256, 0, as_stream(stream)>>>((const float*)x, x_pitch, (const float*)w, (const float*)bias, (__nv_bfloat16*)out,
-                                                                 out_pitch, n_img, H, W, Cout, act, act_alpha, out_scale, n_pix);
+                                                                 out_pitch, n_img, H, W, Cout, act, act_alpha, out_scale, n_quads);
         return check_launch();
       }
     }

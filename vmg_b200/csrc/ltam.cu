@@ -32,7 +32,8 @@ template <int D4>
 __global__ void __launch_bounds__(128) ltam_wins_kernel(const void* q, const void* keys, const void* vals, int dt, long long kv_stride,
                                                         const float* __restrict__ loc, int loc_pitch, const float* __restrict__ rel,
                                                         const float* __restrict__ decay, void* out, int out_dt, int n, int h, int w,
-                                                        int C, int heads, int K, long long n_windows) {
+                                                        int C, int heads, int K, long long n_windows, const float* __restrict__ obias,
+                                                        const void* anchor) {
   constexpr int D = D4 * 4;
   const long long win = (long long)blockIdx.x * 8 + (threadIdx.x >> 4);
   if (win >= n_windows) return;
@@ -92,9 +93,12 @@ __global__ void __launch_bounds__(128) ltam_wins_kernel(const void* q, const voi
   }
   const float inv = 1.f / l;
 #pragma unroll
-  for (int i = 0; i < D4; ++i)
-    st4(out, out_dt, qpix * C + head * D + i * 4,
-        make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv));
+  for (int i = 0; i < D4; ++i) {
+    float4 o = make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
+    if (obias) { const float4 b4 = *reinterpret_cast<const float4*>(obias + head * D + i * 4); o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
+    if (anchor) { const float4 a4 = ld4(anchor, out_dt, qpix * C + head * D + i * 4); o.x += a4.x; o.y += a4.y; o.z += a4.z; o.w += a4.w; }
+    st4(out, out_dt, qpix * C + head * D + i * 4, o);
+  }
 }
 
 
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16
                                                              const __nv_bfloat16* __restrict__ vals, long long kv_stride,
                                                              const float* __restrict__ loc, int loc_pitch, const float* __restrict__ rel,
                                                              const float* __restrict__ decay, void* out, int out_dt, int n, int h, int w,
-                                                             int K, long long n_windows) {
+                                                             int K, long long n_windows, const float* __restrict__ obias, const void* anchor) {
   constexpr int D = D4 * 4, C = 4 * D, ROWB = C * 2, CH = ROWB / 16;     // bytes / 16-byte chunks per row
   constexpr int NST = LTAM_STAGES;
   extern __shared__ __align__(16) uint8_t sm[];                           // [NST stages][2 (k,v)][32 rows][ROWB], then src_s[32][K]
@@ -234,10 +238,14 @@ __global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16
   if (!active) return;
   const float inv = 1.f / l;
 #pragma unroll
-  for (int i = 0; i < D4; ++i)
-    st4(out, out_dt, qpix * C + head * D + i * 4,
-        make_float4(__uint_as_float((uint32_t)acc2[2 * i]) * inv, __uint_as_float((uint32_t)(acc2[2 * i] >> 32)) * inv,
-                    __uint_as_float((uint32_t)acc2[2 * i + 1]) * inv, __uint_as_float((uint32_t)(acc2[2 * i + 1] >> 32)) * inv));
+  for (int i = 0; i < D4; ++i) {
+    float4 o = make_float4(__uint_as_float((uint32_t)acc2[2 * i]) * inv, __uint_as_float((uint32_t)(acc2[2 * i] >> 32)) * inv,
+                           __uint_as_float((uint32_t)acc2[2 * i + 1]) * inv, __uint_as_float((uint32_t)(acc2[2 * i + 1] >> 32)) * inv);
+    // values that were projected at store time (proj is linear and the softmax weights sum to 1): bias and anchor here
+    if (obias) { const float4 b4 = *reinterpret_cast<const float4*>(obias + head * D + i * 4); o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
+    if (anchor) { const float4 a4 = ld4(anchor, out_dt, qpix * C + head * D + i * 4); o.x += a4.x; o.y += a4.y; o.z += a4.z; o.w += a4.w; }
+    st4(out, out_dt, qpix * C + head * D + i * 4, o);
+  }
 }
 
 }  // namespace vmgb
@@ -246,9 +254,10 @@ using namespace vmgb;
 
 extern "C" int vmgb_ltam_wins(const void* q, const void* keys, const void* vals, int dt, long long kv_stride, const float* loc,
                               int loc_pitch, const float* rel, const float* decay, void* out, int out_dt, int n, int h, int w, int C,
-                              int heads, int K, void* stream) {
+                              int heads, int K, const float* out_bias, const void* anchor, void* stream) {
   if (!q || !keys || !vals || !loc || !rel || !decay || !out || !dt_ok(dt) || !dt_ok(out_dt)) return VMGB_EINVAL;
   if (heads != 4 || K <= 0 || (h & 1) || (w & 1) || C % (4 * heads) || 2 * K > loc_pitch) return VMGB_EINVAL;
+  if (out_bias && (reinterpret_cast<uintptr_t>(out_bias) & 15)) return VMGB_EINVAL;
   const long long n_windows = (long long)n * (h / 2) * (w / 2);
   const unsigned blocks = (unsigned)((n_windows + 7) / 8);
   const int D4 = C / heads / 4;
@@ -258,12 +267,12 @@ extern "C" int vmgb_ltam_wins(const void* q, const void* keys, const void* vals,
 #define LAUNCH_S(DD)                                                                                                          \
     if (smem > 48 * 1024) cudaFuncSetAttribute(ltam_wins_smem_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);         \
     ltam_wins_smem_kernel<DD><<<blocks, 128, smem, as_stream(stream)>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)keys,  \
-        (const __nv_bfloat16*)vals, kv_stride, loc, loc_pitch, rel, decay, out, out_dt, n, h, w, K, n_windows)
+        (const __nv_bfloat16*)vals, kv_stride, loc, loc_pitch, rel, decay, out, out_dt, n, h, w, K, n_windows, out_bias, anchor)
     if (D4 == 7) { LAUNCH_S(7); } else { LAUNCH_S(9); }
 #undef LAUNCH_S
     return check_launch();
   }
-#define LAUNCH(DD) ltam_wins_kernel<DD><<<blocks, 128, 0, as_stream(stream)>>>(q, keys, vals, dt, kv_stride, loc, loc_pitch, rel, decay, out, out_dt, n, h, w, C, heads, K, n_windows)
+#define LAUNCH(DD) ltam_wins_kernel<DD><<<blocks, 128, 0, as_stream(stream)>>>(q, keys, vals, dt, kv_stride, loc, loc_pitch, rel, decay, out, out_dt, n, h, w, C, heads, K, n_windows, out_bias, anchor)
   switch (D4) {
     case 4: LAUNCH(4); break;    // C = 64
     case 7: LAUNCH(7); break;    // C = 112 (VMG-REDS)

@@ -325,6 +325,17 @@ class VMG(nn.Module):
             self._packed[key] = ent
         return ent[1]
 
+    def _pc_nobias(self, mod):
+        """Packed weights of a Linear WITHOUT its bias (LTAM value projection, see _trajectory)."""
+        w = mod.weight
+        key = ('nobias', id(mod))
+        ver = (w._version, w.data_ptr(), self.precision)
+        ent = self._packed.get(key)
+        if ent is None or ent[0] != ver:
+            ent = (ver, _ops.pack_conv(w, None, 1, tc=self.precision == 'bf16'))
+            self._packed[key] = ent
+        return ent[1]
+
     # -------------------------------------------------------------------------------------------
     # SPyNet (vmg.py:39-123, 435-464) -- fp32 end to end; only the level-0 flows are consumed
     # -------------------------------------------------------------------------------------------
@@ -462,10 +473,17 @@ class VMG(nn.Module):
         stride = st.key_stride
         kcap = (T + stride - 1) // stride
         step_elems = 2 * n * H * W * C
-        proj = self._pc(tm.LTAM.proj)
+        # LTAM's output projection is applied to the VALUES when a key frame is stored (proj is linear and the softmax weights
+        # sum to 1: proj(sum_j p_j v_j) + b = sum_j p_j proj(v_j) + b): T/stride launches instead of T-1, and the attention
+        # kernel adds the bias and the warped anchor itself (trajectory.py:791-795)
+        # (bf16 path only: the strict-fp32 path keeps the reference's operation order)
+        pre_proj = self.precision == 'bf16'
+        proj = self._pc_nobias(tm.LTAM.proj) if pre_proj else self._pc(tm.LTAM.proj)
+        pbias = tm.LTAM.proj.bias.detach().float().contiguous() if tm.LTAM.proj.bias is not None else None
         rel = tm.LTAM.relative_pos_encoding.detach().contiguous()
         decay = tm.LTAM.decay_v
         fbuf = torch.empty((T, 2 * n, H, W, C), device=x.device, dtype=x.dtype)
+        vproj = torch.empty_like(fbuf) if pre_proj else None     # projected values; only the key-frame steps are written (same stride as the keys)
         loc = [torch.empty((2 * n, H, W, 2 * kcap), device=x.device, dtype=torch.float32) for _ in range(2)]
         o.loc_identity_(loc[0], 0)
         cur_loc, K = 0, 0
@@ -480,13 +498,19 @@ class VMG(nn.Module):
                 flow = fl[j - 1]
                 warped = o.flow_warp_fused(prev, flow, loc[cur_loc], 2 * K, loc[1 - cur_loc], semantics=self._sem)
                 cur_loc = 1 - cur_loc
-                att = o.ltam_wins(qp[j], qp[0], fbuf[0], stride * step_elems, K, loc[cur_loc], rel, decay, st.heads)
-                feat_in = o.linear(att, proj, epi=o.EPI_RESADD, res=warped)
+                if pre_proj:
+                    feat_in = o.ltam_wins(qp[j], qp[0], vproj[0], stride * step_elems, K, loc[cur_loc], rel, decay, st.heads,
+                                          out_bias=pbias, anchor=warped)
+                else:
+                    att = o.ltam_wins(qp[j], qp[0], fbuf[0], stride * step_elems, K, loc[cur_loc], rel, decay, st.heads)
+                    feat_in = o.linear(att, proj, epi=o.EPI_RESADD, res=warped)
                 if is_key:
                     o.loc_identity_(loc[cur_loc], 2 * K)
             if is_key:
                 K += 1                                  # step j becomes key frame K-1 once fbuf[j] is written
             prev = self._resblocks(tm.resblocks, (xp[j], feat_in), fbuf[j], flags, j, scratch)
+            if pre_proj and is_key and j + 1 < T:
+                o.linear(prev, proj, out=vproj[j])
         back, fwd = o.unpair_sweeps(fbuf)               # outputs_back[i] = backward sweep at step T-1-i
         return o.conv2d((back, x, fwd), self._pc(tm.fusion), act=o.ACT_LRELU, alpha=0.1)
 
