@@ -10,6 +10,7 @@ per GPU (torchrun), one clip per rank, no data-path collective (clips are indepe
 ONE JSON line on rank 0:
   value         720p frames/s, inputs resident in HBM (CUDA events, max over ranks)
   e2e           same through the public nn.Module call with pinned-host input and output copies in the timed region
+                (the read-back of step i overlaps the forward of step i+1 on a copy stream; all copies end inside the region)
   roofline      tensor-pipe fraction of the dominant kernel from per-launch CUDA events of one instrumented forward
   cpu_baseline  the CPU oracle (oracle/vmg_oracle.py, a port of the reference forward) on a bounded sample (N=1 only)
   gpu_reference the reference's own arithmetic on this GPU: the oracle restatement (the same ATen / cuDNN calls as
@@ -399,14 +400,25 @@ def main():
             print(json.dumps({'profile_mode': True, 'ms_per_step': ms_step, 'value': value, 'gpu_launches': launches}))
         return
     # ---- end to end: pinned host input -> H2D -> forward -> D2H of the output frames
+    # The read-back of step i (1.1 GB over PCIe) runs on a copy stream while step i+1 computes, into alternating pinned
+    # buffers -- what a serving loop around the public call does; every copy starts and finishes inside the timed region
+    # (the end event waits for the copy stream).
     model(x_host.cuda(non_blocking=True))
+    out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
+    copy_stream = torch.cuda.Stream()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         xd = x_host.cuda(non_blocking=True)
         y = model(xd)
-        out_host.copy_(y, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            out_hosts[i & 1].copy_(y, non_blocking=True)
+            y.record_stream(copy_stream)
+    torch.cuda.current_stream().wait_stream(copy_stream)
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
