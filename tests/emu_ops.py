@@ -168,6 +168,37 @@ def add(a, b):
     return (a.float() + b.float()).to(a.dtype)
 
 
+def add_crop(a, b, H, W):
+    return (a.float() + b.float()).to(a.dtype)[:, :H, :W, :].contiguous()
+
+
+def tab_mix_supported(x, C, chunk_h, chunk_w):
+    """Same predicate as vmg_b200/ops.py (the fused kernel is bf16-only, so the strict-fp32 CPU runs take the separate ops)."""
+    return x.dtype == torch.bfloat16 and x.is_contiguous() and chunk_h == 8 and chunk_w == 8 and C in (64, 112) and x.shape[-1] == C
+
+
+def tab_mix(x, ln_g, ln_b, eps, pcs, phase, B, acc=None, a=None, m_scaling=1.0):
+    """fp32 emulation of csrc/tab_mix.cu out of the separate emulated ops: phase 0 -> per-sample channel sums (as fp32, the
+    fixed-point accumulator of the kernel divided by 2^24), phase 1 -> the new activation."""
+    N, H, W, C = x.shape
+    T = N // B
+    xn = layernorm(x.float(), ln_g, ln_b, eps=eps)
+    br = []
+    for axis, pc in ((0, pcs[0]), (1, pcs[1])):
+        A = morph_gather(xn, 8, axis)
+        Y = linear(A, pc, act=ACT_RELU, out_scale=1.0 / C)
+        br.append(morph_scatter(Y, N, H, W, C, 8, axis))
+    cb = linear(xn, pcs[2], act=ACT_RELU, out_scale=1.0 / C)
+    if phase == 0:
+        return (br[0] + br[1] + cb).view(T, B, H * W, C).sum((0, 2))
+    mix = mix3(br[0], br[1], cb, a, T, B, H * W)
+    return linear(mix, pcs[3], epi=EPI_GATE, res=x.float(), aux=xn, res_scale=m_scaling).to(x.dtype)
+
+
+def fixsum_finalize(acc, scale):
+    return acc.float() * scale
+
+
 def decay_weights_(w, gamma):
     w.mul_(gamma)
     return w
@@ -238,7 +269,7 @@ def flow_smooth(flow, r):
     return f.permute(0, 2, 3, 1).contiguous()
 
 
-def ltam_wins(q, keys0, vals0, kv_stride, K, loc, rel, decay, heads):
+def ltam_wins(q, keys0, vals0, kv_stride, K, loc, rel, decay, heads, out_bias=None, anchor=None):
     """q: [n,h,w,C]; keys0/vals0 are views whose storage offset marks key-frame 0 (see model.py)."""
     n, h, w, C = q.shape
     d = C // heads
@@ -265,6 +296,10 @@ def ltam_wins(q, keys0, vals0, kv_stride, K, loc, rel, decay, heads):
     attn = (logits + pe.reshape(heads, 4, 4 * K)[None, None, None]).softmax(-1)
     o_ = torch.einsum('nyxhqk,nyxhkd->nyxhqd', attn, vv)                        # [n,h/2,w/2,heads,4,d]
     o_ = o_.view(n, h // 2, w // 2, heads, 2, 2, d).permute(0, 1, 4, 2, 5, 3, 6).reshape(n, h, w, C)
+    if out_bias is not None:
+        o_ = o_ + out_bias.float()
+    if anchor is not None:
+        o_ = o_ + anchor.float()
     return o_.to(q.dtype).contiguous()
 
 
