@@ -140,7 +140,7 @@ __device__ __forceinline__ bool pre_ok(const TcP& p, bool pvalid, int g, int nb)
 // ACT / EPI / PS are compile-time for the combinations the model uses (-1 = read from the parameters): the fully
 // generic body is ~2 000 instructions per chunk and thrashed the instruction cache (stall_no_inst); a
 // specialised instance is ~150.
-template <int ACT, int EPI, int PS>
+template <int ACT, int EPI, int PS, bool BIASED = false>
 __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw, bool pvalid, int img, int hh, int ww,
                                                long long pix, int g, int nt, int ch, const float* bias_s, bool have_pre,
                                                const uint4& pre0, const uint4& pre1, uint32_t sdst0 = 0u, uint32_t sdst1 = 0u,
@@ -153,11 +153,16 @@ __device__ __forceinline__ void epilogue_chunk(const TcP& p, const uint32_t* raw
   const int nvalid = min(16, p.Cout_g - nb);
   const int co0 = g * p.Cout_g + nb;
   float v[16];
+  if (BIASED) {                                  // the caller added the bias while it moved the chunk out of the TMEM load registers
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + ch * 16 + 4 * q);     // smem broadcast
-    v[4 * q] = __uint_as_float(raw[4 * q]) + b4.x; v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b4.y;
-    v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b4.z; v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b4.w;
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + ch * 16 + 4 * q);     // smem broadcast
+      v[4 * q] = __uint_as_float(raw[4 * q]) + b4.x; v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b4.y;
+      v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b4.z; v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b4.w;
+    }
   }
   // one warp-uniform switch per chunk (a per-element switch compiles to 16 jump-table branches)
   switch (act) {
@@ -556,7 +561,7 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a1.x), "=r"(a1.y), "=r"(a1.z), "=r"(a1.w) : "r"(c1 + 8u * 4096u) : "memory");
           }
         }
-        epilogue_chunk<ACT, EPI, 0>(p, raw, pvalid, img, hh, ww, pix, g, nt, ch0 + c, bias_s, hp, r0, r1, c0, c1, hp && has_aux, a0, a1);
+        epilogue_chunk<ACT, EPI, 0, true>(p, raw, pvalid, img, hh, ww, pix, g, nt, ch0 + c, bias_s, hp, r0, r1, c0, c1, hp && has_aux, a0, a1);
       };
       uint32_t raw[16], work[16];              // single chunk body, see run_epilogue_t
       __syncwarp();
@@ -564,8 +569,14 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
 #pragma unroll 1
       for (int c = 0; c < chn; ++c) {
         tmem_ld_wait();
+        // the chunk leaves the TMEM load registers THROUGH the bias add (one FADD per element instead of a MOV plus the FADD
+        // later), so the next tcgen05.ld can be issued before the activation math
 #pragma unroll
-        for (int j = 0; j < 16; ++j) work[j] = raw[j];
+        for (int q = 0; q < 4; ++q) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + (ch0 + c) * 16 + 4 * q);
+          work[4 * q] = __float_as_uint(__uint_as_float(raw[4 * q]) + b4.x); work[4 * q + 1] = __float_as_uint(__uint_as_float(raw[4 * q + 1]) + b4.y);
+          work[4 * q + 2] = __float_as_uint(__uint_as_float(raw[4 * q + 2]) + b4.z); work[4 * q + 3] = __float_as_uint(__uint_as_float(raw[4 * q + 3]) + b4.w);
+        }
         __syncwarp();
         if (c + 1 < chn) tmem_ld16_issue(taddr + (ch0 + c + 1) * 16, raw);
         process(c, work);
@@ -578,6 +589,7 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
       // coalesced copy-out of the pass: 4 rows x (up to) 128 contiguous bytes per warp instruction
       const int col = ch0 * 16 + piece * 8;
       const bool cok = tvalid && piece < 2 * chn && nt * p.NT + col + 8 <= p.Cout_g && !(p.dbg & 8);
+      __nv_bfloat16* otile = op0 + pbase * p.out_pitch + col;      // 64-bit once per pass; the offsets inside a tile fit 32 bits
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = crow0 + 4 * i, rr = quarter * 32 + r;
@@ -586,7 +598,7 @@ __device__ __forceinline__ void run_epilogue_w_t(const TcP& p, float* bias_s, ui
           uint4 val;
           const uint32_t src = buf + (uint32_t)r * 128u + (uint32_t)((piece ^ (r & 7)) << 4);
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(src) : "memory");
-          *reinterpret_cast<uint4*>(op0 + (pbase + (long long)dh * p.W + dw) * p.out_pitch + col) = val;
+          *reinterpret_cast<uint4*>(otile + (dh * p.W + dw) * p.out_pitch) = val;
         }
       }
       __syncwarp();                       // buffer free: next pass / next item's residual
