@@ -111,7 +111,9 @@ int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2, int n_src
  * flags / flags_next: two DIFFERENT arrays of n_img * ceil(H/16) * (W/16) 32-bit counters.  `flags` must be all zero on
  * entry; the kernel leaves it dirty and zeroes `flags_next`, so consecutive calls alternate the two arrays.
  * Cross-tile (halo) dependencies between layers are tracked through these counters instead of grid barriers.
- * Takes C % 16 == 0, C <= 128, W % 16 == 0; VMGB_EUNSUPPORTED otherwise (the caller issues vmgb_conv2d_nhwc_tc per layer). */
+ * Takes C % 16 == 0 with C <= 128 (one output-channel slice) or C in {144, 160} (two slices of 80 columns computed by
+ * different clusters from the same activations), W % 16 == 0; VMGB_EUNSUPPORTED otherwise (the caller issues
+ * vmgb_conv2d_nhwc_tc per layer). */
 int vmgb_resblock_chain(void* y_inout, void* y_alt, void* t_tmp, void* out, const void* w_layers, int Kp, const float* bias_layers,
                         void* flags, void* flags_next, int n_img, int H, int W, int C, int n_blocks, float res_scale, void* stream);
 

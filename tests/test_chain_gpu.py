@@ -35,6 +35,9 @@ CASES = [
     (1, 64, 112, 128, 2),       # C = 128, W = 112
     (3, 24, 16, 112, 2),        # a single pair per tile row, ragged last tile row
     (4, 180, 320, 112, 2),      # more tile rows than clusters / 3: equal raster ranges instead of row-aligned ownership
+    (2, 184, 320, 144, 15),     # the few-levels trajectory step: C = 144 as two output-channel slices of 80 (37 tile clusters x 2 slices)
+    (1, 40, 48, 144, 3),        # two slices, one pair per cluster
+    (2, 72, 80, 160, 2),        # C = 160: both slices full
 ]
 
 
@@ -81,8 +84,8 @@ def test_chain_bit_identical_to_per_layer_launches(case):
 
 
 def test_chain_unsupported_shapes_take_the_per_layer_path():
-    pc, _ = make_chain(144, 1, seed=5)             # C = 144: two N slices -> not a chain shape
-    x = rnd(1, 32, 32, 144, seed=2).bfloat16().to(DEV)
+    pc, _ = make_chain(192, 1, seed=5)             # C = 192: more than two slices -> not a chain shape
+    x = rnd(1, 32, 32, 192, seed=2).bfloat16().to(DEV)
     assert not ops.resblock_chain_supported(pc, x)
     out = torch.empty_like(x)
     y = ops.resblock_chain(x.clone(), pc, 0.1, out, None, None)

@@ -149,7 +149,7 @@ def run_tab(iters, frames=25):
 def run_chain(iters):
     """The 15-block residual chain of one trajectory step: ONE persistent kernel vs 30 per-layer launches."""
     flush = torch.zeros(64 * 1024 * 1024, device=DEV)
-    for n, H, W, C, nb in ((2, 184, 320, 112, 15), (2, 128, 128, 112, 15), (2, 184, 320, 144, 15)):
+    for n, H, W, C, nb in ((2, 184, 320, 112, 15), (2, 128, 128, 112, 15), (2, 184, 320, 144, 15), (2, 128, 128, 144, 15)):
         layers = [ops.pack_conv(torch.randn(C, C, 3, 3, device=DEV) * 0.03, torch.randn(C, device=DEV) * 0.1, 1, tc=True) for _ in range(2 * nb)]
         pc = ops.pack_resblock_chain(layers)
         x = torch.randn(n, H, W, C, device=DEV).bfloat16()

@@ -39,6 +39,7 @@ struct ChainP {
   int n_img, H, W, C;
   int tiles_h, pairs_w;               // 16 x 8 tiles; a pair = two horizontally adjacent tiles (rank 0 left, rank 1 right)
   int n_layers, nkb, ra, a_unit_bytes, b_stage_bytes;
+  int slices, NT;                     // output channels in `slices` slices of NT columns (NT % 16 == 0): C <= 128 -> 1 x C, C = 144 -> 2 x 80
   int n_pairs, n_clusters, segs;      // segs > 0: row-aligned ownership (cluster = (tile row, segment)); 0: equal raster ranges
   const float* bias;                  // [n_layers][C]
   __nv_bfloat16* buf[4];              // 0 / 1: the block ping-pong (buf[0] holds the chain input), 2: conv1 output, 3: final output
@@ -49,7 +50,7 @@ struct ChainP {
 };
 
 constexpr int CH_THREADS = 448;
-constexpr int CH_MAX_BOXES = 18;       // 9 taps x 2 K blocks
+constexpr int CH_MAX_BOXES = 27;       // 9 taps x up to 3 K blocks
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
@@ -112,7 +113,7 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   const uint32_t wfull0 = aempty0 + 8 * p.ra;
   const uint32_t tfull0 = wfull0 + 8 * CH_MAX_BOXES, tempty0 = tfull0 + 16;
   const uint32_t rfull = tempty0 + 16, wfree0 = rfull + 8;      // wfree0 + 8 * kb: the weight boxes of K block kb may be replaced
-  const uint32_t tmem_slot = wfree0 + 24;      // keeps bias_s (tmem_slot + 16) 16-byte aligned
+  const uint32_t tmem_slot = wfree0 + 32;      // 3 wfree barriers + pad: keeps bias_s (tmem_slot + 16) 16-byte aligned
   const uint32_t dep_ready = tmem_slot + 4, pub_cnt = tmem_slot + 8, res_cnt = tmem_slot + 12;      // progress counters
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));      // [2][128]: layer parity
@@ -126,7 +127,7 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
     for (int i = 0; i < nboxes; ++i) mbar_init(wfull0 + 8 * i, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 512); }
     mbar_init(rfull, 1);
-    mbar_init(wfree0, 1); mbar_init(wfree0 + 8, 1);
+    mbar_init(wfree0, 1); mbar_init(wfree0 + 8, 1); mbar_init(wfree0 + 16, 1);
     tmem_slot_ptr[1] = 0u; tmem_slot_ptr[2] = 0u; tmem_slot_ptr[3] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
@@ -141,11 +142,14 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int cl = blockIdx.x >> 1;
+  // cluster = (run of tile pairs, output-channel slice): the slices of a pair are computed by different clusters from the
+  // same activations; a pair of layer l is complete when all 2 * slices CTAs have published it
+  const int cl = (blockIdx.x >> 1) / p.slices, slice = (blockIdx.x >> 1) - cl * p.slices;
   int p0, p1;
   chain_range(p, cl, p0, p1);
   const int n_own = p1 - p0;
-  const int NT = p.C, NH = p.C >> 1;
+  const int NT = p.NT, NH = p.NT >> 1;
+  const int cbase = slice * NT;                       // first output channel of this slice
   const int NL = p.n_layers;
 
   auto tile_of = [&](int pair, int& img, int& h0, int& w0) {
@@ -195,7 +199,7 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         if (kb == 0) {
           // bias of layer l: its buffer was last read by the epilogue of layer l-2, and the last tile of layer l-1 (whose
           // MMAs have started) depended on the last tile of layer l-2 having been drained
-          for (int c = lane; c < NT; c += 32) bias_s[(l & 1) * 128 + c] = __ldg(p.bias + (long long)l * p.C + c);
+          for (int c = lane; c < NT; c += 32) bias_s[(l & 1) * 128 + c] = cbase + c < p.C ? __ldg(p.bias + (long long)l * p.C + cbase + c) : 0.f;
           __threadfence_block();
           __syncwarp();
         }
@@ -203,7 +207,9 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
           for (int tap = 0; tap < TAPS; ++tap) {
             const int box = kb * TAPS + tap;
             if (rank == 0) mbar_expect_tx(wfull0 + 8 * box, (uint32_t)(2 * NH * 128));
-            tma_load_2d_2sm(w_base + box * p.b_stage_bytes, &mapB, wfull0_l + 8 * box, kb * 64, (l * TAPS + tap) * p.C + (int)rank * NH);
+            // rows past the slice's real channels (cbase + .. >= C) belong to the next tap: finite garbage in accumulator columns
+            // that are never stored (past the tensor end the box is zero-filled)
+            tma_load_2d_2sm(w_base + box * p.b_stage_bytes, &mapB, wfull0_l + 8 * box, kb * 64, (l * TAPS + tap) * p.C + cbase + (int)rank * NH);
           }
         }
         __syncwarp();
@@ -270,7 +276,7 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
     // ===================== dependency checker (both CTAs): runs ahead of the producer, never blocked by the ring =====================
     pdl_wait();                                       // this launch's counters were zeroed by the previous launch
     for (int l = 1; l < NL; ++l) {
-      const unsigned need = 2u * (unsigned)l;         // layer l-1 of the 3 x 3 pair neighbourhood is in memory (both tiles of each pair)
+      const unsigned need = 2u * (unsigned)p.slices * (unsigned)l;   // layer l-1 of the 3 x 3 pair neighbourhood is in memory (both tiles, every slice)
       for (int s = 0; s < n_own; ++s) {
         const int pair = p0 + chain_order(n_own, s);
         const int row = pair / p.pairs_w, pc = pair - row * p.pairs_w, img = row / p.tiles_h, th = row - img * p.tiles_h;
@@ -315,7 +321,7 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         if (elect_one()) {
           fence_proxy_async();
           mbar_expect_tx(rfull, 128u * row_bytes);
-          tma_load_4d(res_s, mR, rfull, 0, w0, h0, img);
+          tma_load_4d(res_s, mR, rfull, cbase, w0, h0, img);
         }
         __syncwarp();
       }
@@ -397,8 +403,8 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            if (pvalid) {
-              uint4* o = reinterpret_cast<uint4*>(outp + pix * p.C + ch * 16);
+            if (pvalid && cbase + ch * 16 < p.C) {
+              uint4* o = reinterpret_cast<uint4*>(outp + pix * p.C + cbase + ch * 16);
               o[0] = pack8(v); o[1] = pack8(v + 8);
             }
             ch += 2; ++i;
@@ -455,7 +461,7 @@ extern "C" int vmgb_resblock_chain(void* y_inout, void* y_alt, void* t_tmp, void
                                    void* flags, void* flags_next, int n_img, int H, int W, int C, int n_blocks, float res_scale, void* stream) {
   if (!y_inout || !y_alt || !t_tmp || !out || !w_layers || !bias_layers || !flags || !flags_next || flags == flags_next) return VMGB_EINVAL;
   if (n_img < 1 || H < 8 || W < 8 || n_blocks < 1 || Kp < C || (Kp & 15)) return VMGB_EINVAL;
-  if ((C & 15) || C > 128 || (W & 15)) return VMGB_EUNSUPPORTED;       // one N slice of <= 128 columns; pairs must not straddle rows
+  if ((C & 15) || C > 160 || (W & 15)) return VMGB_EUNSUPPORTED;       // <= 2 slices of <= 128 columns; pairs must not straddle rows
   const void* ptrs[5] = {y_inout, y_alt, t_tmp, out, w_layers};
   for (const void* q : ptrs) if (reinterpret_cast<uintptr_t>(q) & 15) return VMGB_EINVAL;
   std::call_once(g_chain_once, chain_init);
@@ -465,12 +471,15 @@ extern "C" int vmgb_resblock_chain(void* y_inout, void* y_alt, void* t_tmp, void
 
   ChainP p;
   p.n_img = n_img; p.H = H; p.W = W; p.C = C;
+  p.slices = C <= 128 ? 1 : 2;
+  p.NT = ((C + p.slices - 1) / p.slices + 15) / 16 * 16;               // 144 -> 2 x 80
   p.tiles_h = (H + 15) / 16; p.pairs_w = W / 16;
   p.n_layers = 2 * n_blocks; p.nkb = (C + 63) / 64;
   p.a_unit_bytes = (18 * 10 * 128 + 1023) / 1024 * 1024;
-  p.b_stage_bytes = (C / 2) * 128;
+  p.b_stage_bytes = (p.NT / 2) * 128;
+  if (p.b_stage_bytes & 1023) return VMGB_EUNSUPPORTED;                // SWIZZLE_128B atoms: NT / 2 a multiple of 8
   p.n_pairs = n_img * p.tiles_h * p.pairs_w;
-  const int max_cl = g_sms / 2;
+  const int max_cl = (g_sms / 2) / p.slices;
   const int rows = n_img * p.tiles_h;
   const int per = (p.n_pairs + max_cl - 1) / max_cl;
   const int segs = (p.pairs_w + per - 1) / per;
@@ -480,8 +489,10 @@ extern "C" int vmgb_resblock_chain(void* y_inout, void* y_alt, void* t_tmp, void
   p.buf[0] = (__nv_bfloat16*)y_inout; p.buf[1] = (__nv_bfloat16*)y_alt; p.buf[2] = (__nv_bfloat16*)t_tmp; p.buf[3] = (__nv_bfloat16*)out;
   p.flags = (unsigned*)flags; p.flags_next = (unsigned*)flags_next;
   p.res_scale = res_scale; p.zero = 0;
+  if (p.nkb * 9 > CH_MAX_BOXES) return VMGB_EUNSUPPORTED;
   const int wbytes = (p.nkb * 9 * p.b_stage_bytes + 1023) / 1024 * 1024;
-  const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + 1024 /*bias*/ + 128 + 128 * C * 2 /*residual box*/ + 256;
+  // after the 1024-byte alignment: ring, weights, barriers + counters (16 * ra + 320 <= 512), bias [2][128], residual box
+  const int fixed = 1023 + 512 + 1024 + 128 + 128 * p.NT * 2;
   p.ra = (g_smem - wbytes - fixed) / p.a_unit_bytes;
   if (p.ra > 6) p.ra = 6;
   if (p.ra < 2) return VMGB_EUNSUPPORTED;
@@ -494,18 +505,18 @@ extern "C" int vmgb_resblock_chain(void* y_inout, void* y_alt, void* t_tmp, void
     cuuint32_t box[4] = {64, 10, 18, 1};
     if (!enc_bf16(&mA[i], p.buf[i], 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return VMGB_EINVAL;
     if (i < 2) {
-      cuuint32_t rbox[4] = {(cuuint32_t)C, 8, 16, 1};
+      cuuint32_t rbox[4] = {(cuuint32_t)p.NT, 8, 16, 1};
       if (!enc_bf16(&mR[i], p.buf[i], 4, dims, str, rbox, CU_TENSOR_MAP_SWIZZLE_NONE)) return VMGB_EINVAL;
     }
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)p.n_layers * 9 * C};
     cuuint64_t str[1] = {(cuuint64_t)Kp * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(C / 2)};
+    cuuint32_t box[2] = {64, (cuuint32_t)(p.NT / 2)};
     if (!enc_bf16(&mB, w_layers, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return VMGB_EINVAL;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(2 * p.n_clusters)); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
+  cfg.gridDim = dim3((unsigned)(2 * p.n_clusters * p.slices)); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;

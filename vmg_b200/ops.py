@@ -187,7 +187,7 @@ def pack_resblock_chain(layers):
 
 
 def resblock_chain_supported(pc, y):
-    return (pc.wtc is not None and y.dtype == torch.bfloat16 and y.is_contiguous() and pc.C % 16 == 0 and pc.C <= 128 and
+    return (pc.wtc is not None and y.dtype == torch.bfloat16 and y.is_contiguous() and pc.C % 16 == 0 and (pc.C <= 128 or pc.C in (144, 160)) and
             y.shape[2] % 16 == 0 and y.shape[1] >= 8 and y.shape[-1] == pc.C)
 
 
