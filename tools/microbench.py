@@ -43,6 +43,9 @@ def conv_cases():
         ('traj_res_112_b4_store', 4, 184, 320, 112, 112, 3, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
         ('tiny_1round_112', 1, 64, 296, 112, 112, 3, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
         ('ffn_fc1_g4_112', 25, 184, 320, 112, 672, 3, 4, 1, ops.EPI_STORE, ops.ACT_GELU, 0),
+        ('ffn_fc1_g4_112_relu', 25, 184, 320, 112, 672, 3, 4, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
+        ('ffn_fc1_g4_112_none', 25, 184, 320, 112, 672, 3, 4, 1, ops.EPI_STORE, ops.ACT_NONE, 0),
+        ('ffn_fc1_L1_g4_224', 25, 92, 160, 224, 1344, 3, 4, 1, ops.EPI_STORE, ops.ACT_GELU, 0),
         ('ffn_fc2_672to112', 1, 1, 25 * 184 * 320, 672, 112, 1, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
         ('linear_112', 1, 1, 25 * 184 * 320, 112, 112, 1, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
         ('gate_proj_112', 1, 1, 25 * 184 * 320, 112, 112, 1, 1, 1, ops.EPI_GATE, ops.ACT_NONE, 0),
