@@ -36,6 +36,7 @@ struct TcP {
   int out_smem;                                // bytes of the output staging tile [128][NT+8] bf16 (0 = direct stores)
   int aux_smem;                                // bytes of the gate-operand staging buffer (GATE epilogue; 0 = off)
   int wst;                                     // 1 = warp-private transposition staging epilogue (run_epilogue_w), 32 KB
+  int v8;                                      // 1 = direct 32-byte-store epilogue (run_epilogue_v8: plain store, bf16 output)
   int res_tma;                                 // 1 = residual tile fetched by TMA one item ahead (run_epilogue_rtma, CTA-pair kernel)
   int zero;                                    // always 0, opaque to the compiler (forces data dependencies, see run_epilogue_rtma)
   int dbg;                                     // bottleneck probes (tools/microbench.py): 1 = no MMA, 2 = no drain, 4 = no activation loads
@@ -628,6 +629,124 @@ __device__ __forceinline__ void run_epilogue_w(const TcP& p, float* bias_s, uint
   VMGB_EPIW_CASE(VMGB_ACT_NONE, VMGB_EPI_STORE)
 #undef VMGB_EPIW_CASE
   run_epilogue_w_t<-1, -1>(p, bias_s, tmem_base, tfull0, tempty0, first, step, total, warp, lane, origin, tempty_cluster0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Plain-store epilogue with DIRECT 32-byte stores (bf16 output, no residual, no pixel shuffle).  tcgen05.ld 32x32b hands a
+// thread 16 consecutive columns of ITS row = 32 contiguous output bytes, which sm_100 stores with one STG.256: no staging
+// buffer, no copy-out pass, full 32-byte sectors.  The FFN fc1 launch (7.9 GB of hidden tensor, bound by its drain and
+// behind it by the 3.94 TB/s write-only HBM rate) spent 3.8 of its 19.4 instructions per element in the staged copy-out
+// and its address arithmetic.  32-byte alignment: the chunk grid starts at the first column whose global channel is a
+// multiple of 16 (`head` = 0 or 8: grouped convs with Cout_g = 168 start odd groups 16 bytes off); the 8-column head /
+// tail pieces go out as 16-byte stores.
+// ---------------------------------------------------------------------------------------------
+template <int ACT>
+__device__ __forceinline__ void v8_act(const TcP& p, float* v, int n) {
+  if (ACT == VMGB_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) if (j < n) v[j] = fmaxf(v[j], 0.f);
+  } else if (ACT == VMGB_ACT_LRELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) if (j < n) v[j] = v[j] > 0.f ? v[j] : v[j] * p.alpha;
+  } else if (ACT == VMGB_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) if (j < n) gelu_tanh2(v[j], v[j + 1]);
+  }
+  if (p.out_scale != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) if (j < n) v[j] *= p.out_scale;
+  }
+}
+
+template <int ACT, class Origin>
+__device__ __forceinline__ void run_epilogue_v8_t(const TcP& p, float* bias_s, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                                  long long first, long long step, long long total, int warp, int lane, Origin origin,
+                                                  uint32_t tempty_cluster0) {
+  const int ew = warp - 4, quarter = warp & 3, half = ew >> 2;
+  const int row = quarter * 32 + lane;
+  const int bw_shift = 31 - __clz(p.BW), bw_mask = p.BW - 1;
+  __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+  uint32_t acc_phase0 = 0, acc_phase1 = 0;
+  int it = 0, bias_combo = -1;
+  for (long long t = first; t < total; t += step, ++it) {
+    const int as = it & 1;
+    int combo, img, h0, w0; bool tvalid;
+    origin(t, combo, img, h0, w0, tvalid);
+    const int nt = combo % p.nt_per_g, g = combo / p.nt_per_g;
+    const int hh = h0 + (row >> bw_shift), ww = w0 + (row & bw_mask);
+    const bool pvalid = tvalid && hh < p.H && ww < p.W;
+    const uint32_t aph = as ? acc_phase1 : acc_phase0;
+    if (as) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_STRIDE;
+    if (combo != bias_combo) {                                            // bias of this (group, N tile) -> smem
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int c = ew * 32 + lane; c < p.NT; c += 256) {
+        const int nb = nt * p.NT + c;
+        bias_s[c] = (p.bias && nb < p.Cout_g) ? __ldg(p.bias + g * p.Cout_g + nb) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      bias_combo = combo;
+    }
+    // column geometry: local column 0 is global channel cbase; 32-byte pieces start where the global channel is a multiple of 16
+    const int cbase = g * p.Cout_g + nt * p.NT;
+    const int ncols = min(p.NT, p.Cout_g - nt * p.NT);
+    const int head = (16 - (cbase & 15)) & 15;                            // 0 or 8 (host: Cout_g % 8 == 0)
+    const int nfull = (ncols - head) >> 4, tail = ncols - head - 16 * nfull;
+    const int n0 = (nfull + 1) >> 1;
+    const int lo = half ? n0 : 0, hi = half ? nfull : n0;
+    __nv_bfloat16* orow = outp + (((long long)img * p.H + hh) * p.W + ww) * p.out_pitch + cbase;
+    mbar_wait(tfull0 + 8 * as, aph);
+    tc_fence_after();
+    if (!(p.dbg & 2)) {
+      uint32_t raw[16];
+      float v[16];
+      int k = lo;
+      __syncwarp();
+      if (k < hi) tmem_ld16_issue(taddr + head + k * 16, raw);
+#pragma unroll 1
+      while (k < hi) {
+        tmem_ld_wait();
+        const float* bk = bias_s + head + k * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bk + 4 * q);
+          v[4 * q] = __uint_as_float(raw[4 * q]) + b4.x; v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b4.y;
+          v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b4.z; v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b4.w;
+        }
+        __syncwarp();
+        if (k + 1 < hi) tmem_ld16_issue(taddr + head + (k + 1) * 16, raw);      // next chunk in flight during the activation math
+        v8_act<ACT>(p, v, 16);
+        if (pvalid) stg_v8(orow + head + k * 16, pack8(v), pack8(v + 8));
+        ++k;
+      }
+      const int piece = half ? tail : head;                               // the 8-column piece of this column half (16-byte store)
+      if (piece) {
+        const int col = half ? head + 16 * nfull : 0;
+        uint32_t r8[8];
+        __syncwarp();
+        tmem_ld8_issue(taddr + col, r8);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r8[j]) + bias_s[col + j];
+        v8_act<ACT>(p, v, 8);
+        if (pvalid) *reinterpret_cast<uint4*>(orow + col) = pack8(v);
+      }
+    }
+    tc_fence_before();
+    if (tempty_cluster0) mbar_arrive_cluster(tempty_cluster0 + 8 * as); else mbar_arrive(tempty0 + 8 * as);
+  }
+}
+
+template <class Origin>
+__device__ __forceinline__ void run_epilogue_v8(const TcP& p, float* bias_s, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                                long long first, long long step, long long total, int warp, int lane, Origin origin,
+                                                uint32_t tempty_cluster0 = 0) {
+  switch (p.act) {
+    case VMGB_ACT_GELU: run_epilogue_v8_t<VMGB_ACT_GELU>(p, bias_s, tmem_base, tfull0, tempty0, first, step, total, warp, lane, origin, tempty_cluster0); break;
+    case VMGB_ACT_RELU: run_epilogue_v8_t<VMGB_ACT_RELU>(p, bias_s, tmem_base, tfull0, tempty0, first, step, total, warp, lane, origin, tempty_cluster0); break;
+    case VMGB_ACT_LRELU: run_epilogue_v8_t<VMGB_ACT_LRELU>(p, bias_s, tmem_base, tfull0, tempty0, first, step, total, warp, lane, origin, tempty_cluster0); break;
+    default: run_epilogue_v8_t<VMGB_ACT_NONE>(p, bias_s, tmem_base, tfull0, tempty0, first, step, total, warp, lane, origin, tempty_cluster0); break;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1237,6 +1356,17 @@ conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
                           h0 = (rem / p.tiles_w) * 16; w0 = (rem % p.tiles_w) * 8;
                         },
                         mapa_rank(tempty0, 0));
+    else if (p.v8)
+      run_epilogue_v8(p, bias_s, tmem_base, tfull0, tempty0, first, step, n_pairs, warp, lane,
+                      [&](long long t, int& cmb, int& img, int& h0, int& w0, bool& valid) {
+                        const long long mt = 2 * t + rank;
+                        cmb = combo;
+                        valid = mt < n_mt;
+                        img = valid ? (int)(mt / tiles_per_img) : 0;
+                        const int rem = valid ? (int)(mt % tiles_per_img) : 0;
+                        h0 = (rem / p.tiles_w) * 16; w0 = (rem % p.tiles_w) * 8;
+                      },
+                      mapa_rank(tempty0, 0));
     else if (p.wst)
       run_epilogue_w(p, bias_s, tmem_base, tfull0, tempty0, first, step, n_pairs, warp, lane,
                      [&](long long t, int& cmb, int& img, int& h0, int& w0, bool& valid) {
@@ -1285,6 +1415,7 @@ static int g_pdl = 1;         // VMGB_PDL=0 turns programmatic dependent launch 
 static int g_split_n = 1;     // VMGB_SPLIT_N=0: keep N <= 256 linears in one N tile (A/B switch)
 static int g_res_tma = 1;     // VMGB_RES_TMA=0: residual of the pair kernel by per-thread cp.async instead of TMA (A/B switch)
 static int g_ws2_multi = 1;   // VMGB_WS2_MULTI=0: multi-source convs stay on the per-tap kernel (A/B switch)
+static int g_v8 = 1;          // VMGB_V8=0: staged copy-out instead of the direct 32-byte-store epilogue (A/B switch)
 static int g_wst_gate = 1;    // VMGB_WST_GATE=0: gate epilogue on the per-thread staging path (A/B switch)
 static int g_no_wst = 0;      // VMGB_NO_WST=1: A/B switch (tools/microbench.py) for the warp-private staging epilogue
 static int g_device = -1;     // the device tc_init ran on: attributes / SM count are per device, other devices are refused
@@ -1299,6 +1430,7 @@ static void tc_init() {
   if (const char* e = getenv("VMGB_WS2_MULTI")) g_ws2_multi = atoi(e);
   if (const char* e = getenv("VMGB_RES_TMA")) g_res_tma = atoi(e);
   if (const char* e = getenv("VMGB_SPLIT_N")) g_split_n = atoi(e);
+  if (const char* e = getenv("VMGB_V8")) g_v8 = atoi(e);
   if (const char* e = getenv("VMGB_WST_GATE")) g_wst_gate = atoi(e);      // A/B switch for tools/microbench.py
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1384,7 +1516,7 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   p.bias = (const float*)bias; p.out = out; p.res = res; p.aux = aux;
   p.out_dt = out_dt; p.out_pitch = out_pitch; p.res_dt = res_dt; p.res_pitch = res_pitch; p.aux_dt = aux_dt; p.aux_pitch = aux_pitch;
   p.act = act; p.alpha = act_alpha; p.out_scale = out_scale; p.epi = epi; p.res_scale = res_scale; p.ps = pixel_shuffle;
-  p.dbg = 0; p.zero = 0; p.wst = 0; p.res_tma = 0;
+  p.dbg = 0; p.zero = 0; p.wst = 0; p.v8 = 0; p.res_tma = 0;
   p.nsub = 0; p.ra = 0; p.rb = 0; p.a_unit_bytes = 0; p.a_sbo = 0; p.res_smem = 0; p.out_smem = 0; p.aux_smem = 0;
   const int budget = g_smem_optin - 1024 - 512 - 1024;     // alignment slack, barriers, bias staging
 
@@ -1424,6 +1556,8 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
     if (best_slices && clusters_max >= 1 && nbars <= WS2_MAX_BOXES_HOST && (variant == 13 || worth)) {       // weight-box barriers in the kernel
       p.nt_per_g = best_slices; p.NT = best_nt; p.b_stage_bytes = (best_nt / 2) * 128; p.ra = best_ra; p.out_smem = best_out;
       p.wst = best_wst; p.res_smem = best_wst ? 0 : best_res;
+      p.v8 = g_v8 && epi == VMGB_EPI_STORE && out_dt == VMGB_BF16 && pixel_shuffle == 0 && (out_pitch & 15) == 0 && (Cout_g & 7) == 0 &&
+             !(reinterpret_cast<uintptr_t>(out) & 31) && (act == VMGB_ACT_NONE || act == VMGB_ACT_RELU || act == VMGB_ACT_LRELU || act == VMGB_ACT_GELU);
       p.BH = 16; p.BW = 8; p.a_unit_bytes = ubytes; p.stages = 0;
       p.tiles_h = (H + 15) / 16; p.tiles_w = (W + 7) / 8;
       p.total_tiles = n_mt * groups * p.nt_per_g;
