@@ -1556,7 +1556,8 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
     if (best_slices && clusters_max >= 1 && nbars <= WS2_MAX_BOXES_HOST && (variant == 13 || worth)) {       // weight-box barriers in the kernel
       p.nt_per_g = best_slices; p.NT = best_nt; p.b_stage_bytes = (best_nt / 2) * 128; p.ra = best_ra; p.out_smem = best_out;
       p.wst = best_wst; p.res_smem = best_wst ? 0 : best_res;
-      p.v8 = g_v8 && epi == VMGB_EPI_STORE && out_dt == VMGB_BF16 && pixel_shuffle == 0 && (out_pitch & 15) == 0 && (Cout_g & 7) == 0 &&
+      // (3x3 only: the 7x7 SPyNet layers with 16-64 output channels measured 15 % slower on it than on the staged copy-out)
+      p.v8 = g_v8 && R == 3 && epi == VMGB_EPI_STORE && out_dt == VMGB_BF16 && pixel_shuffle == 0 && (out_pitch & 15) == 0 && (Cout_g & 7) == 0 &&
              !(reinterpret_cast<uintptr_t>(out) & 31) && (act == VMGB_ACT_NONE || act == VMGB_ACT_RELU || act == VMGB_ACT_LRELU || act == VMGB_ACT_GELU);
       p.BH = 16; p.BW = 8; p.a_unit_bytes = ubytes; p.stages = 0;
       p.tiles_h = (H + 15) / 16; p.tiles_w = (W + 7) / 8;
