@@ -404,8 +404,7 @@ resblock_chain_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
             }
             if (pvalid && cbase + ch * 16 < p.C) {
-              uint4* o = reinterpret_cast<uint4*>(outp + pix * p.C + cbase + ch * 16);
-              o[0] = pack8(v); o[1] = pack8(v + 8);
+              stg_v8(outp + pix * p.C + cbase + ch * 16, pack8(v), pack8(v + 8));      // one 32-byte store (STG.256): C % 16 == 0, 32-byte aligned buffers
             }
             ch += 2; ++i;
           }
@@ -463,7 +462,7 @@ extern "C" int vmgb_resblock_chain(void* y_inout, void* y_alt, void* t_tmp, void
   if (n_img < 1 || H < 8 || W < 8 || n_blocks < 1 || Kp < C || (Kp & 15)) return VMGB_EINVAL;
   if ((C & 15) || C > 160 || (W & 15)) return VMGB_EUNSUPPORTED;       // <= 2 slices of <= 128 columns; pairs must not straddle rows
   const void* ptrs[5] = {y_inout, y_alt, t_tmp, out, w_layers};
-  for (const void* q : ptrs) if (reinterpret_cast<uintptr_t>(q) & 15) return VMGB_EINVAL;
+  for (const void* q : ptrs) if (reinterpret_cast<uintptr_t>(q) & 31) return VMGB_EINVAL;       // 32-byte stores / TMA boxes
   std::call_once(g_chain_once, chain_init);
   if (!g_enc || g_sms < 2) return VMGB_EUNSUPPORTED;
   int cur = -1;
