@@ -462,7 +462,8 @@ extern "C" int vmgb_resblock_chain(void* y_inout, void* y_alt, void* t_tmp, void
   if (n_img < 1 || H < 8 || W < 8 || n_blocks < 1 || Kp < C || (Kp & 15)) return VMGB_EINVAL;
   if ((C & 15) || C > 160 || (W & 15)) return VMGB_EUNSUPPORTED;       // <= 2 slices of <= 128 columns; pairs must not straddle rows
   const void* ptrs[5] = {y_inout, y_alt, t_tmp, out, w_layers};
-  for (const void* q : ptrs) if (reinterpret_cast<uintptr_t>(q) & 31) return VMGB_EINVAL;       // 32-byte stores / TMA boxes
+  for (const void* q : ptrs) if (reinterpret_cast<uintptr_t>(q) & 15) return VMGB_EINVAL;
+  for (const void* q : ptrs) if (reinterpret_cast<uintptr_t>(q) & 31) return VMGB_EUNSUPPORTED;   // 32-byte stores: the caller takes the per-layer path
   std::call_once(g_chain_once, chain_init);
   if (!g_enc || g_sms < 2) return VMGB_EUNSUPPORTED;
   int cur = -1;
