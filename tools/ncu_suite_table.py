@@ -10,6 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rows = list(csv.reader(open(sys.argv[1])))
 names = [l.split()[1] for l in open(sys.argv[2]) if l.startswith('ran ')] if len(sys.argv) > 2 else []
 h, units = rows[0], rows[1]
+rows = rows[:2] + [r for r in rows[2:] if 'finalize' not in r[h.index('Kernel Name')]]      # helper kernels are not cases
 ci = {n: i for i, n in enumerate(h)}
 peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('hbm_gbs', 6446.3) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6446.3
 
@@ -42,6 +43,7 @@ for r in rows[2:]:
     if tp != tp and 'sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active' in ci:
         tp = val(r, 'sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active')
     ia = val(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active') if 'smsp__issue_active.avg.pct_of_peak_sustained_active' in ci else float('nan')
-    idx = int(r[ci['ID']])
+    idx = k
+    k += 1
     case = names[idx - (len(rows) - 2 - len(names))] if names and idx >= len(rows) - 2 - len(names) else '(setup)'
     print(f"| {idx} | {case} | `{kn[:44]}` | {us:.1f} | {(rd + wr) / 1e6:.1f} | | {gbs:.0f} | {gbs / peak:.2f} | {tp:.1f} | {ia:.1f} | {r[ci['launch__registers_per_thread']]} | {r[ci['launch__grid_size']]} x {r[ci['launch__block_size']]} |")
