@@ -305,3 +305,35 @@ def test_error_codes():
     with pytest.raises(RuntimeError):
         ops.ltam_wins(x, x, x, 0, 1, torch.zeros(1, 4, 4, 2, device=DEV), torch.zeros(3, 4, 4, device=DEV),
                       torch.zeros(3, device=DEV), 3)
+
+
+@pytest.mark.parametrize('C', [224, 448])
+def test_resample_up_short_rows(C):
+    """The half-/quarter-warp-per-row up-sampling LayerNorm (F = C/4 = 56 / 112, bf16, with and without the skip add)."""
+    xr = rnd(3, 6, 10, C, seed=21).bfloat16()
+    ad = rnd(3, 6, 10, C, seed=22).bfloat16()
+    gg, bb = rnd(C // 4, seed=23), rnd(C // 4, seed=24)
+    for add_ in (ad, None):
+        out = ops.resample_ln(xr.to(DEV), None if add_ is None else add_.to(DEV), gg.to(DEV), bb.to(DEV), True)
+        close(out, emu.resample_ln(xr, add_, gg, bb, True), 4e-2)
+
+
+def test_add_crop():
+    a, b = rnd(3, 24, 16, 112, seed=41).bfloat16(), rnd(3, 24, 16, 112, seed=42).bfloat16()
+    ref = (a.float() + b.float()).bfloat16()
+    for H, W in ((24, 16), (20, 16), (21, 13)):
+        out = ops.add_crop(a.to(DEV), b.to(DEV), H, W)
+        assert out.shape == (3, H, W, 112) and out.is_contiguous()
+        assert torch.equal(out.cpu(), ref[:, :H, :W, :])
+    x32 = rnd(2, 8, 8, 12, seed=43)                      # fp32 / C % 8 != 0: add + slice
+    assert torch.equal(ops.add_crop(x32.to(DEV), x32.to(DEV), 6, 8).cpu(), (x32 + x32)[:, :6, :8, :])
+
+
+def test_rgb_input_conv():
+    """3 -> C input conv (register-resident kernel, W % 4 == 0) against the emulation, borders included."""
+    w, b = rnd(112, 3, 3, 3, seed=51, scale=0.3), rnd(112, seed=52, scale=0.2)
+    x = rnd(2, 48, 48, 3, seed=53)                        # >= 4096 pixels: the dedicated kernel
+    pc = ops.pack_conv(w.to(DEV), b.to(DEV), 1, tc=False)
+    out = ops.conv2d(x.to(DEV), pc, act=ops.ACT_LRELU, alpha=0.01, out_dtype=torch.bfloat16, use_tc=False)
+    ref = emu.conv2d(x, emu.pack_conv(w, b), act=ops.ACT_LRELU, alpha=0.01)
+    close(out, ref, 2e-2)
