@@ -378,26 +378,28 @@ class VMG(nn.Module):
         o = _ops
         N, H, W, C = x.shape
         sm = blk.spatial_mixing
+        # in-place decay of the two token-mixer weights, once per forward (function.py:765-768 / 778-781), then their packed copies
+        for lin, gamma in ((sm.mlp_h[0], sm.gamma_h), (sm.mlp_w[0], sm.gamma_w)):
+            o.decay_weights_(lin.weight.data, gamma)
+        pc_h, pc_w = self._pc(sm.mlp_h[0], force=True), self._pc(sm.mlp_w[0], force=True)
         if self.channel_mixer == 'vanilla' and o.tab_mix_supported(x, C, sm.chunk_h, sm.chunk_w):
             # fused mixing half (csrc/tab_mix.cu): LayerNorm, both Morph-FC token mixers, the channel mixer, the global
             # mean, the 3-way mix, the gated projection and the residual in two passes over x
-            for lin, gamma in ((sm.mlp_h[0], sm.gamma_h), (sm.mlp_w[0], sm.gamma_w)):
-                o.decay_weights_(lin.weight.data, gamma)                 # function.py:765-768 / 778-781
-            pcs = (self._pc(sm.mlp_h[0], force=True), self._pc(sm.mlp_w[0], force=True), self._pc(sm.mlp_c[0]), self._pc(sm.proj))
+            pcs = (pc_h, pc_w, self._pc(sm.mlp_c[0]), self._pc(sm.proj))
             acc = o.tab_mix(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, pcs, 0, B)
-            a = o.fixsum_finalize(acc, 1.0 / (T * H * W))                # function.py:791
-            a = o.linear(a, self._pc(sm.reweight.fc1, tc=False), act=o.ACT_GELU, use_tc=False)
-            a = o.softmax3(o.linear(a, self._pc(sm.reweight.fc2, tc=False), use_tc=False))
-            x = o.tab_mix(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, pcs, 1, B, a=a, m_scaling=self.m_scaling)
-            return self._tab_ffn(blk, x)
+            if acc is not None:                                          # None: the library does not take this shape on this device
+                a = o.fixsum_finalize(acc, 1.0 / (T * H * W))            # function.py:791
+                a = o.linear(a, self._pc(sm.reweight.fc1, tc=False), act=o.ACT_GELU, use_tc=False)
+                a = o.softmax3(o.linear(a, self._pc(sm.reweight.fc2, tc=False), use_tc=False))
+                y = o.tab_mix(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, pcs, 1, B, a=a, m_scaling=self.m_scaling)
+                if y is not None:
+                    return self._tab_ffn(blk, y)
         xn = o.layernorm(x, blk.norm2.weight, blk.norm2.bias)
         branches = []
-        for axis, (lin, gamma, chunk, Cp) in enumerate(((sm.mlp_h[0], sm.gamma_h, sm.chunk_h, sm.Ch),
-                                                        (sm.mlp_w[0], sm.gamma_w, sm.chunk_w, sm.Cw))):
-            o.decay_weights_(lin.weight.data, gamma)                     # function.py:765-768 / 778-781
+        for axis, (pcl, chunk, Cp) in enumerate(((pc_h, sm.chunk_h, sm.Ch), (pc_w, sm.chunk_w, sm.Cw))):
             A = o.morph_gather(xn, chunk, axis)
             Y = torch.empty_strided(A.shape, A.stride(), device=A.device, dtype=A.dtype)   # same (16-byte padded) row pitch
-            o.linear(A, self._pc(lin, force=True), act=o.ACT_RELU, out_scale=1.0 / Cp, out=Y)
+            o.linear(A, pcl, act=o.ACT_RELU, out_scale=1.0 / Cp, out=Y)
             branches.append(o.morph_scatter(Y, N, H, W, C, chunk, axis))
             del A, Y
         h, w = branches
