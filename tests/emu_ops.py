@@ -285,8 +285,10 @@ def ltam_wins(q, keys0, vals0, kv_stride, K, loc, rel, decay, heads, out_bias=No
     ly = loc[..., 1:2 * K:2].round().long()
     bi = torch.arange(n)[:, None, None, None].expand(n, h, w, K)
     ki = torch.arange(K)[None, None, None, :].expand(n, h, w, K)
-    kg = keys[ki, bi, ly, lx]                             # [n,h,w,K,C]
-    vg = vals[ki, bi, ly, lx]
+    inb = ((lx >= 0) & (lx < w) & (ly >= 0) & (ly < h)).float()[..., None]     # padding_mode='zeros': a zero key / value row
+    lx, ly = lx.clamp(0, w - 1), ly.clamp(0, h - 1)
+    kg = keys[ki, bi, ly, lx] * inb                       # [n,h,w,K,C]
+    vg = vals[ki, bi, ly, lx] * inb
     qq = (q.float() * (d ** -0.5)).view(n, h // 2, 2, w // 2, 2, heads, d).permute(0, 1, 3, 5, 2, 4, 6).reshape(n, h // 2, w // 2, heads, 4, d)
     kk = kg.view(n, h // 2, 2, w // 2, 2, K, heads, d).permute(0, 1, 3, 6, 5, 2, 4, 7).reshape(n, h // 2, w // 2, heads, 4 * K, d)
     vv = vg.view(n, h // 2, 2, w // 2, 2, K, heads, d).permute(0, 1, 3, 6, 5, 2, 4, 7).reshape(n, h // 2, w // 2, heads, 4 * K, d)

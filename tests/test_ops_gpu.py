@@ -264,6 +264,28 @@ def test_ltam_wins(C, dtype, tol):
         close(out2, ref + bias + anchor.float(), 2 * tol)
 
 
+@pytest.mark.parametrize('C', [112, 144])
+def test_ltam_wins_corner_cases(C):
+    """A window count that is not a multiple of the 8 windows of a block, sampling locations outside the frame (zero rows
+    that still take part in the softmax: padding_mode='zeros'), position terms large enough to move the lazy softmax
+    reference point many times, more key frames than ring stages."""
+    n, h, w, heads, T = 1, 6, 10, 4, 7
+    feats = rnd(T, n, h, w, C, seed=21).to(torch.bfloat16)
+    keys = emu.l2norm(rnd(T, n, h, w, C, seed=22)).to(torch.bfloat16)
+    decay = 1 - 2 ** (-2 - torch.arange(heads - 1, -1, -1, dtype=torch.float32))
+    fe = n * h * w * C
+    dk, dv = keys.to(DEV), feats.to(DEV)
+    for K, rel_scale in ((7, 0.05), (7, 30.0), (5, 8.0), (2, 30.0)):
+        rel = rnd(heads, 4, 4, seed=23 + K, scale=rel_scale)
+        g = torch.Generator().manual_seed(5 + K)
+        loc = torch.zeros(n, h, w, 2 * T)
+        loc[..., 0:2 * K:2] = torch.randint(-2, w + 2, (n, h, w, K), generator=g).float()
+        loc[..., 1:2 * K:2] = torch.randint(-2, h + 2, (n, h, w, K), generator=g).float()
+        ref = emu.ltam_wins(keys[3], keys[0], feats[0], fe, K, loc, rel, decay, heads)
+        out = ops.ltam_wins(dk[3], dk[0], dv[0], fe, K, loc.to(DEV), rel.to(DEV), decay.to(DEV), heads)
+        close(out, ref, 2e-2)
+
+
 def test_spynet_helpers_and_io():
     B, T, H, W = 2, 3, 66, 70
     x = torch.rand(B, T, 3, H, W, generator=torch.Generator().manual_seed(1))

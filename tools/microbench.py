@@ -180,6 +180,32 @@ def run_chain(iters):
                               'tflops': round(fl / ms / 1e9, 1)}), flush=True)
 
 
+def run_ltam(iters):
+    """LTAM at the headline trajectory shape (2 images of 184 x 320, C = 112) with flow-like sampling locations
+    (identity + a few pixels of jitter, some outside the frame), projection bias and anchor as in the model."""
+    flush = torch.zeros(64 * 1024 * 1024, device=DEV)
+    n, H, W, C, T = 2, 184, 320, 112, 34
+    g = torch.Generator(device='cpu').manual_seed(0)
+    keys = torch.nn.functional.normalize(torch.randn(T, n, H, W, C, generator=g), dim=-1).bfloat16().to(DEV)
+    vals = torch.randn(T, n, H, W, C, generator=g).bfloat16().to(DEV)
+    loc = torch.zeros(n, H, W, 2 * T, device=DEV)
+    for k in range(T):
+        ops.loc_identity_(loc, 2 * k)
+    loc += (torch.randn(n, H, W, 2 * T, generator=g) * 3).round().to(DEV)
+    rel = (torch.randn(4, 4, 4, generator=g) * 0.05).to(DEV)
+    dec = torch.full((4,), 0.97, device=DEV)
+    anchor = vals[1]
+    bias = torch.zeros(C, device=DEV)
+    outs = {}
+    for K in (1, 4, 9, 17, 33):
+        fn = lambda K=K: ops.ltam_wins(keys[0], keys[0], vals[0], n * H * W * C, K, loc, rel, dec, 4, out_bias=bias, anchor=anchor)
+        ms = timeit(fn, iters, flush)
+        outs[K] = fn().float()
+        nb = (2 * K * C + 3 * C) * n * H * W * 2
+        print(json.dumps({'case': f'ltam_K{K}', 'ms': round(ms, 4), 'GBps': round(nb / ms / 1e6, 1),
+                          'checksum': float(outs[K].double().abs().mean())}), flush=True)
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('what', nargs='?', default='all')
@@ -195,5 +221,7 @@ if __name__ == '__main__':
         run_chain(a.iters)
     if a.what in ('tab', 'all'):
         run_tab(a.iters)
+    if a.what == 'ltam':
+        run_ltam(a.iters)
     if a.what == 'tab_small':
         run_tab(1, frames=4)
