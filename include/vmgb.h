@@ -218,10 +218,6 @@ int vmgb_l2norm(const void* x, int x_dt, int x_pitch, void* out, int out_dt, lon
  * q      [n,h,w,C]            L2-normalised current features
  * keys   [Kcap][n,h,w,C]      L2-normalised key-frame stage inputs   (first K used)
  * vals   [Kcap][n,h,w,C]      key-frame propagated features
- *        key frame k of either tensor starts kv_stride ELEMENTS after key frame k-1; consecutive pixels of a key frame
- *        are kv_pitch elements apart (>= C, a multiple of 8): the bf16 model path keeps the keys and the values of a pixel
- *        in ONE 512-byte record (keys at channel 0, values at channel 128) so that each gathered row is two aligned
- *        128-byte lines and both rows of a sampling location share a DRAM page (profiles/r2_ltam_ncu.md)
  * loc    fp32 [n,h,w,loc_pitch] tracked (x,y) per key-frame, channels 2k,2k+1
  * rel    fp32 [heads][4][4], decay fp32 [heads]
  * out    [n,h,w,C]  attention output BEFORE the proj Linear (proj + anchor add = conv2d RESADD), or -- with
@@ -229,7 +225,7 @@ int vmgb_l2norm(const void* x, int x_dt, int x_pitch, void* out, int out_dt, lon
  *        ALREADY PROJECTED (vals_k = proj.weight . sparse_k, one launch per key frame instead of one per step; exact
  *        in real arithmetic because proj is linear and the softmax weights sum to 1: trajectory.py:791-795), out_bias =
  *        proj.bias (fp32 [C], 16-byte aligned) and anchor = the warped propagated feature (dtype out_dt, pitch C). */
-int vmgb_ltam_wins(const void* q, const void* keys, const void* vals, int dt, long long kv_stride, int kv_pitch,
+int vmgb_ltam_wins(const void* q, const void* keys, const void* vals, int dt, long long kv_stride,
                    const float* loc, int loc_pitch, const float* rel, const float* decay,
                    void* out, int out_dt, int n, int h, int w, int C, int heads, int K,
                    const float* out_bias, const void* anchor, void* stream);

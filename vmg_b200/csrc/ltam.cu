@@ -29,7 +29,7 @@ __device__ __forceinline__ unsigned long long lt_unpack(uint32_t w) {
 }
 
 template <int D4>
-__global__ void __launch_bounds__(128) ltam_wins_kernel(const void* q, const void* keys, const void* vals, int dt, long long kv_stride, int kv_pitch,
+__global__ void __launch_bounds__(128) ltam_wins_kernel(const void* q, const void* keys, const void* vals, int dt, long long kv_stride,
                                                         const float* __restrict__ loc, int loc_pitch, const float* __restrict__ rel,
                                                         const float* __restrict__ decay, void* out, int out_dt, int n, int h, int w,
                                                         int C, int heads, int K, long long n_windows, const float* __restrict__ obias,
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(128) ltam_wins_kernel(const void* q, const voi
       const float2 lc = *reinterpret_cast<const float2*>(loc + pj * loc_pitch + 2 * k);
       const int sx = (int)rintf(lc.x), sy = (int)rintf(lc.y);
       const bool inb = sx >= 0 && sx < w && sy >= 0 && sy < h;    // padding_mode='zeros'
-      const long long src = (long long)k * kv_stride + (((long long)img * h + sy) * w + sx) * kv_pitch + head * D;
+      const long long src = (long long)k * kv_stride + (((long long)img * h + sy) * w + sx) * C + head * D;
       float dot = 0.f;
       if (inb) {
 #pragma unroll
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(128) ltam_wins_kernel(const void* q, const voi
 constexpr int LTAM_STAGES = 3;      // measured: 3 stages (47 KB, 4 blocks per SM) beat 4 stages (62 KB, 3 blocks) by ~8 %
 template <int D4>
 __global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ keys,
-                                                             const __nv_bfloat16* __restrict__ vals, long long kv_stride, int kv_pitch,
+                                                             const __nv_bfloat16* __restrict__ vals, long long kv_stride,
                                                              const float* __restrict__ loc, int loc_pitch, const float* __restrict__ rel,
                                                              const float* __restrict__ decay, void* out, int out_dt, int n, int h, int w,
                                                              int K, long long n_windows, const float* __restrict__ obias, const void* anchor) {
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16
       const uint32_t dk = (uint32_t)__cvta_generic_to_shared(base + r * ROWB + cc * 16);
       const uint32_t dv = dk + 32 * ROWB;
       if (sp >= 0) {
-        const long long src = (long long)k * kv_stride + (long long)sp * kv_pitch + cc * 8;
+        const long long src = (long long)k * kv_stride + (long long)sp * C + cc * 8;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dk), "l"(keys + src) : "memory");
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dv), "l"(vals + src) : "memory");
       } else {
@@ -252,27 +252,27 @@ __global__ void __launch_bounds__(128) ltam_wins_smem_kernel(const __nv_bfloat16
 
 using namespace vmgb;
 
-extern "C" int vmgb_ltam_wins(const void* q, const void* keys, const void* vals, int dt, long long kv_stride, int kv_pitch, const float* loc,
+extern "C" int vmgb_ltam_wins(const void* q, const void* keys, const void* vals, int dt, long long kv_stride, const float* loc,
                               int loc_pitch, const float* rel, const float* decay, void* out, int out_dt, int n, int h, int w, int C,
                               int heads, int K, const float* out_bias, const void* anchor, void* stream) {
   if (!q || !keys || !vals || !loc || !rel || !decay || !out || !dt_ok(dt) || !dt_ok(out_dt)) return VMGB_EINVAL;
-  if (heads != 4 || K <= 0 || (h & 1) || (w & 1) || C % (4 * heads) || 2 * K > loc_pitch || kv_pitch < C) return VMGB_EINVAL;
+  if (heads != 4 || K <= 0 || (h & 1) || (w & 1) || C % (4 * heads) || 2 * K > loc_pitch) return VMGB_EINVAL;
   if (out_bias && (reinterpret_cast<uintptr_t>(out_bias) & 15)) return VMGB_EINVAL;
   const long long n_windows = (long long)n * (h / 2) * (w / 2);
   const unsigned blocks = (unsigned)((n_windows + 7) / 8);
   const int D4 = C / heads / 4;
-  if (dt == VMGB_BF16 && !(((uintptr_t)keys | (uintptr_t)vals) & 15) && (kv_stride & 7) == 0 && (kv_pitch & 7) == 0 && (D4 == 7 || D4 == 9)) {
+  if (dt == VMGB_BF16 && !(((uintptr_t)keys | (uintptr_t)vals) & 15) && (kv_stride & 7) == 0 && (D4 == 7 || D4 == 9)) {
     const int smem = LTAM_STAGES * 2 * 32 * C * 2 + 32 * K * 4;
     if (smem > 200 * 1024) return VMGB_EUNSUPPORTED;
 #define LAUNCH_S(DD)                                                                                                          \
     if (smem > 48 * 1024) cudaFuncSetAttribute(ltam_wins_smem_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);         \
     ltam_wins_smem_kernel<DD><<<blocks, 128, smem, as_stream(stream)>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)keys,  \
-        (const __nv_bfloat16*)vals, kv_stride, kv_pitch, loc, loc_pitch, rel, decay, out, out_dt, n, h, w, K, n_windows, out_bias, anchor)
+        (const __nv_bfloat16*)vals, kv_stride, loc, loc_pitch, rel, decay, out, out_dt, n, h, w, K, n_windows, out_bias, anchor)
     if (D4 == 7) { LAUNCH_S(7); } else { LAUNCH_S(9); }
 #undef LAUNCH_S
     return check_launch();
   }
-#define LAUNCH(DD) ltam_wins_kernel<DD><<<blocks, 128, 0, as_stream(stream)>>>(q, keys, vals, dt, kv_stride, kv_pitch, loc, loc_pitch, rel, decay, out, out_dt, n, h, w, C, heads, K, n_windows, out_bias, anchor)
+#define LAUNCH(DD) ltam_wins_kernel<DD><<<blocks, 128, 0, as_stream(stream)>>>(q, keys, vals, dt, kv_stride, loc, loc_pitch, rel, decay, out, out_dt, n, h, w, C, heads, K, n_windows, out_bias, anchor)
   switch (D4) {
     case 4: LAUNCH(4); break;    // C = 64
     case 7: LAUNCH(7); break;    // C = 112 (VMG-REDS)

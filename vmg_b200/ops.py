@@ -574,9 +574,8 @@ def flow_smooth(flow, r):
     return out
 
 
-def ltam_wins(q, keys0, vals0, kv_stride, K, loc, rel, decay, heads, out_bias=None, anchor=None, kv_pitch=None):
-    """keys0 / vals0: tensors whose data_ptr is key-frame 0; key-frame k lives kv_stride elements later, consecutive
-    pixels of a key frame kv_pitch elements apart (default C: dense frames).
+def ltam_wins(q, keys0, vals0, kv_stride, K, loc, rel, decay, heads, out_bias=None, anchor=None):
+    """keys0 / vals0: tensors whose data_ptr is key-frame 0; key-frame k lives kv_stride elements later.
     out_bias / anchor: see include/vmgb.h (values stored already projected)."""
     require_device()
     n, h, w, C = q.shape
@@ -584,7 +583,7 @@ def ltam_wins(q, keys0, vals0, kv_stride, K, loc, rel, decay, heads, out_bias=No
     assert anchor is None or (anchor.is_contiguous() and anchor.shape == q.shape and anchor.dtype == q.dtype)
     assert out_bias is None or (out_bias.dtype == torch.float32 and out_bias.is_contiguous() and out_bias.numel() == C)
     out = torch.empty_like(q)
-    _ck(lib().vmgb_ltam_wins(q.data_ptr(), keys0.data_ptr(), vals0.data_ptr(), _dt(q), kv_stride, kv_pitch or C, loc.data_ptr(),
+    _ck(lib().vmgb_ltam_wins(q.data_ptr(), keys0.data_ptr(), vals0.data_ptr(), _dt(q), kv_stride, loc.data_ptr(),
                              loc.shape[-1], rel.data_ptr(), decay.data_ptr(), out.data_ptr(), _dt(out), n, h, w, C,
                              heads, K, _ptr(out_bias), _ptr(anchor), _stream()), 'vmgb_ltam_wins')
     return out
