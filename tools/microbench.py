@@ -51,6 +51,10 @@ def conv_cases():
         ('gate_proj_112', 1, 1, 25 * 184 * 320, 112, 112, 1, 1, 1, ops.EPI_GATE, ops.ACT_NONE, 0),
         ('gate_proj_224', 1, 1, 25 * 92 * 160, 224, 224, 1, 1, 1, ops.EPI_GATE, ops.ACT_NONE, 0),
         ('linear_448', 1, 1, 100 * 23 * 40, 448, 448, 1, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
+        ('linear_224', 1, 1, 100 * 92 * 160, 224, 224, 1, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
+        ('linear_224_L2', 1, 1, 100 * 46 * 80, 224, 224, 1, 1, 1, ops.EPI_STORE, ops.ACT_RELU, 0),
+        ('ffn_fc2_672to112_100f', 1, 1, 100 * 184 * 320, 672, 112, 1, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
+        ('ffn_fc2_L1_1344to224', 1, 1, 25 * 92 * 160, 1344, 224, 1, 1, 1, ops.EPI_RESADD, ops.ACT_NONE, 0),
         ('upconv2_112to256_ps', 4, 360, 640, 112, 256, 3, 1, 1, ops.EPI_STORE, ops.ACT_LRELU, 2),
         ('hrconv_64', 2, 720, 1280, 64, 64, 3, 1, 1, ops.EPI_STORE, ops.ACT_LRELU, 0),
         ('conv_last_64to3', 2, 720, 1280, 64, 3, 3, 1, 1, ops.EPI_STORE, ops.ACT_NONE, 0),

@@ -1415,6 +1415,7 @@ static int g_pdl = 1;         // VMGB_PDL=0 turns programmatic dependent launch 
 static int g_split_n = 1;     // VMGB_SPLIT_N=0: keep N <= 256 linears in one N tile (A/B switch)
 static int g_res_tma = 1;     // VMGB_RES_TMA=0: residual of the pair kernel by per-thread cp.async instead of TMA (A/B switch)
 static int g_ws2_multi = 1;   // VMGB_WS2_MULTI=0: multi-source convs stay on the per-tap kernel (A/B switch)
+static int g_ws2_lin = 1;     // VMGB_WS2_LIN=0: Linears stay on the per-tap kernel (A/B switch)
 static int g_v8 = 1;          // VMGB_V8=0: staged copy-out instead of the direct 32-byte-store epilogue (A/B switch)
 static int g_wst_gate = 1;    // VMGB_WST_GATE=0: gate epilogue on the per-thread staging path (A/B switch)
 static int g_no_wst = 0;      // VMGB_NO_WST=1: A/B switch (tools/microbench.py) for the warp-private staging epilogue
@@ -1431,6 +1432,7 @@ static void tc_init() {
   if (const char* e = getenv("VMGB_RES_TMA")) g_res_tma = atoi(e);
   if (const char* e = getenv("VMGB_SPLIT_N")) g_split_n = atoi(e);
   if (const char* e = getenv("VMGB_V8")) g_v8 = atoi(e);
+  if (const char* e = getenv("VMGB_WS2_LIN")) g_ws2_lin = atoi(e);
   if (const char* e = getenv("VMGB_WST_GATE")) g_wst_gate = atoi(e);      // A/B switch for tools/microbench.py
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1445,6 +1447,7 @@ static void tc_init() {
     cudaFuncSetAttribute(conv3x3_ws_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
     cudaFuncSetAttribute(conv3x3_ws2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
     cudaFuncSetAttribute(conv3x3_ws2_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+    cudaFuncSetAttribute(conv3x3_ws2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
   }
 }
 
@@ -1523,12 +1526,18 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
   // ---- CTA-pair weight-stationary 3x3 kernel (variant 13, or auto): grouped single-source convs, or ungrouped with up
   //      to 3 equally wide sources (virtual concat)
   if (variant >= 32) { p.dbg = (variant >> 5) & 15; variant = 13; }      // probes: 13 + 32*dbg
-  if (R == S && (R == 3 || R == 7) && H >= 8 && W >= 8 && (n_src == 1 || (groups == 1 && (g_ws2_multi || variant == 13))) &&
+  // A Linear ([1,1,rows,K] "image", rows % 8 == 0) takes the same kernel with R = 1: the rows are read as an [rows/8, 8] image,
+  // a 16 x 8 tile = 128 consecutive rows.  The per-tap kernel re-streams the weights with every 128-row tile (C = 224:
+  // 100 KB of weights per 57 KB of activations through the L2 -> SM fabric, 0.63 of the HBM rate); here they are resident.
+  const bool lin1 = R == 1 && S == 1 && H == 1 && n_img == 1 && (W & 7) == 0 && W >= 128 && n_src == 1 && groups == 1 && pixel_shuffle == 0 &&
+                    (epi == VMGB_EPI_STORE || (epi == VMGB_EPI_RESADD && Cout <= 128) || variant == 13) && g_ws2_lin;
+  const int Hc = lin1 ? W / 8 : H, Wc = lin1 ? 8 : W;
+  if (R == S && (R == 3 || R == 7 || lin1) && Hc >= 8 && Wc >= 8 && (n_src == 1 || (groups == 1 && (g_ws2_multi || variant == 13))) &&
       (variant == 0 || variant == 13)) {
     const int ubytes = ((16 + R - 1) * (8 + R - 1) * 128 + 1023) / 1024 * 1024;
     const int nboxes = R * R * n_src * p.kb_per_src;      // SWIZZLE_128B weight boxes {64 k, NT/2 rows}
     const int nbars = nboxes / (R == 3 ? 1 : R);
-    const long long n_mt = (long long)n_img * ((H + 15) / 16) * ((W + 7) / 8);
+    const long long n_mt = (long long)n_img * ((Hc + 15) / 16) * ((Wc + 7) / 8);
     const long long n_pairs = (n_mt + 1) / 2;
     int best_slices = 0, best_nt = 0, best_ra = 0, best_res = 0, best_out = 0, best_wst = 0;
     for (int sl = 1; sl <= 8 && !best_slices; ++sl) {
@@ -1552,15 +1561,19 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       if (ra >= 2) { best_slices = sl; best_nt = nts; best_ra = ra > 6 ? 6 : ra; best_res = resb; best_out = outb; best_wst = wst; }
     }
     const long long clusters_max = (g_num_sms / 2) / (groups * (best_slices ? best_slices : 1));
-    const bool worth = best_slices && clusters_max >= 1 && n_pairs >= 3 * clusters_max && n_src * p.kb_per_src <= 4;
+    // (Linears: measured wins with the whole weight matrix resident in one slice, K <= 768: 112 / 224 / 448-wide layers 0.84 -> 0.90
+    //  of the HBM rate, FFN fc2 672 -> 112 -9 %; 1344 -> 224 needs two slices and loses)
+    const bool worth = best_slices && clusters_max >= 1 && n_pairs >= 3 * clusters_max &&
+                       (lin1 ? (best_slices == 1 && p.kb_per_src <= 12) : n_src * p.kb_per_src <= 4);
     if (best_slices && clusters_max >= 1 && nbars <= WS2_MAX_BOXES_HOST && (variant == 13 || worth)) {       // weight-box barriers in the kernel
       p.nt_per_g = best_slices; p.NT = best_nt; p.b_stage_bytes = (best_nt / 2) * 128; p.ra = best_ra; p.out_smem = best_out;
       p.wst = best_wst; p.res_smem = best_wst ? 0 : best_res;
       // (3x3 only: the 7x7 SPyNet layers with 16-64 output channels measured 15 % slower on it than on the staged copy-out)
-      p.v8 = g_v8 && R == 3 && epi == VMGB_EPI_STORE && out_dt == VMGB_BF16 && pixel_shuffle == 0 && (out_pitch & 15) == 0 && (Cout_g & 7) == 0 &&
+      p.v8 = g_v8 && R != 7 && epi == VMGB_EPI_STORE && out_dt == VMGB_BF16 && pixel_shuffle == 0 && (out_pitch & 15) == 0 && (Cout_g & 7) == 0 &&
              !(reinterpret_cast<uintptr_t>(out) & 31) && (act == VMGB_ACT_NONE || act == VMGB_ACT_RELU || act == VMGB_ACT_LRELU || act == VMGB_ACT_GELU);
       p.BH = 16; p.BW = 8; p.a_unit_bytes = ubytes; p.stages = 0;
-      p.tiles_h = (H + 15) / 16; p.tiles_w = (W + 7) / 8;
+      p.H = Hc; p.W = Wc;
+      p.tiles_h = (Hc + 15) / 16; p.tiles_w = (Wc + 7) / 8;
       p.total_tiles = n_mt * groups * p.nt_per_g;
       CUtensorMap mA[3], mB, mR;
       // resblock conv2 (no activation, bf16 residual and output): the residual tile comes by TMA into the same 128 x NT
@@ -1569,8 +1582,8 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
                   out_dt == VMGB_BF16 && res_dt == VMGB_BF16 && pixel_shuffle == 0 && (Cout_g & 15) == 0 && (res_pitch & 7) == 0 &&
                   (out_pitch & 7) == 0 && !(reinterpret_cast<uintptr_t>(res) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15) && best_nt <= 128;
       if (p.res_tma) {
-        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
-        cuuint64_t str[3] = {(cuuint64_t)res_pitch * 2, (cuuint64_t)W * res_pitch * 2, (cuuint64_t)H * W * res_pitch * 2};
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wc, (cuuint64_t)Hc, (cuuint64_t)n_img};
+        cuuint64_t str[3] = {(cuuint64_t)res_pitch * 2, (cuuint64_t)Wc * res_pitch * 2, (cuuint64_t)Hc * Wc * res_pitch * 2};
         cuuint32_t box[4] = {(cuuint32_t)best_nt, 8, 16, 1};
         if (!encode_bf16(&mR, res, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) p.res_tma = 0;
       }
@@ -1580,8 +1593,8 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
         for (int s = 0; s < 3; ++s) {
           const void* ptr = s < n_src ? srcs[s] : x;
           if (reinterpret_cast<uintptr_t>(ptr) & 15) return VMGB_EINVAL;
-          cuuint64_t dims[4] = {(cuuint64_t)c_extent, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
-          cuuint64_t str[3] = {(cuuint64_t)x_pitch * 2, (cuuint64_t)W * x_pitch * 2, (cuuint64_t)H * W * x_pitch * 2};
+          cuuint64_t dims[4] = {(cuuint64_t)c_extent, (cuuint64_t)Wc, (cuuint64_t)Hc, (cuuint64_t)n_img};
+          cuuint64_t str[3] = {(cuuint64_t)x_pitch * 2, (cuuint64_t)Wc * x_pitch * 2, (cuuint64_t)Hc * Wc * x_pitch * 2};
           cuuint32_t box[4] = {64, (cuuint32_t)(8 + R - 1), (cuuint32_t)(16 + R - 1), 1};
           if (!encode_bf16(&mA[s], ptr, 4, dims, str, box)) return VMGB_EINVAL;
         }
@@ -1606,7 +1619,8 @@ extern "C" int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2
       cfg.attrs = at; cfg.numAttrs = (g_pdl && !g_pack_pending) ? 2 : 1;
       g_pack_pending = 0;
       cudaError_t e = R == 3 ? cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel<3>, mA[0], mA[1], mA[2], mB, mR, p)
-                             : cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel<7>, mA[0], mA[1], mA[2], mB, mR, p);
+                    : R == 7 ? cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel<7>, mA[0], mA[1], mA[2], mB, mR, p)
+                             : cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel<1>, mA[0], mA[1], mA[2], mB, mR, p);
       if (e != cudaSuccess) { g_last_cuda_error = (int)e; return VMGB_ECUDA; }
       return check_launch();
     }
