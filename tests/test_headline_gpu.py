@@ -107,6 +107,41 @@ def test_headline_linears_and_gate():
         check(out.float(), ref.float(), torch.bfloat16)
 
 
+@pytest.mark.parametrize('case', [
+    # rows, Cin, Cout, act, epi, out dtype, pitched output
+    (100 * 92 * 160, 224, 224, ops.ACT_RELU, ops.EPI_STORE, torch.bfloat16, False),     # level-1 token / channel Linear of the headline step
+    (8 * 7400, 224, 224, ops.ACT_RELU, ops.EPI_STORE, torch.bfloat16, False),           # 463 tiles: odd tail pair, last tile 8 of 16 row groups
+    (8 * 7400 + 8, 112, 112, ops.ACT_NONE, ops.EPI_STORE, torch.bfloat16, True),        # projected LTAM values written into a pitched slice
+    (8 * 7400, 448, 224, ops.ACT_NONE, ops.EPI_STORE, torch.float32, False),            # resampling Linear, fp32 output (staged epilogue)
+    (25 * 184 * 320, 672, 112, ops.ACT_NONE, ops.EPI_RESADD, torch.bfloat16, False),    # FFN fc2 of level 0 + residual
+    (8 * 7400, 672, 112, ops.ACT_NONE, ops.EPI_RESADD, torch.bfloat16, False),
+], ids=lambda c: f'{c[0]}x{c[1]}to{c[2]}')
+def test_linear_on_pair_kernel_bit_identical_to_per_tap(case):
+    """Linears with one resident N slice take the CTA-pair weight-stationary kernel (conv_tc.cu, R = 1: rows as an [rows/8, 8]
+    image).  Same K order and epilogue arithmetic as the per-tap kernel -> required bit-identical, and within the bf16 bound of
+    the fp32 reference."""
+    rows, Cin, Cout, act, epi, odt, pitched = case
+    w = rnd(Cout, Cin, seed=1, scale=Cin ** -0.5).bfloat16().float()
+    b = rnd(Cout, seed=2, scale=0.5)
+    pc = ops.pack_conv(w.to(DEV), b.to(DEV), 1, tc=True)
+    x = rnd(rows, Cin, seed=3).bfloat16().to(DEV)
+    res = rnd(rows, Cout, seed=4).bfloat16().to(DEV) if epi != ops.EPI_STORE else None
+    outs = []
+    for variant in (0, 1):
+        if pitched:
+            buf = torch.zeros(rows, 2 * Cout + 16, device=DEV, dtype=odt)
+            o = buf[:, 16:16 + Cout]
+        else:
+            o = torch.empty(rows, Cout, device=DEV, dtype=odt)
+        ops.linear(x, pc, act=act, epi=epi, res=res, out=o, tc_variant=variant)
+        outs.append(o.float().clone())
+        if pitched:
+            assert buf[:, :16].abs().max().item() == 0 and buf[:, 16 + Cout:].abs().max().item() == 0      # nothing outside the slice
+    assert torch.equal(outs[0], outs[1])
+    ref = emu.linear(x, emu.pack_conv(w.to(DEV), b.to(DEV)), act=act, epi=epi, res=res, out_dtype=torch.float32)
+    check(outs[0], ref.float(), odt)
+
+
 def _tie_flows(n, h, w, seed):
     """Flows on a 1/8 grid (many coordinates land exactly on .5 ties) mixed with continuous and 4x4-block-constant ones."""
     g = torch.Generator().manual_seed(seed)
