@@ -89,7 +89,8 @@ int vmgb_conv2d_nhwc(const void* x, const void* x1, const void* x2, int n_src, i
  * variant: 0 = automatic kernel choice (what the model uses); the others force one kernel for tests and
  * tools/microbench.py and return VMGB_EUNSUPPORTED (-2) when that kernel does not take the shape:
  *   1 = per-tap ring kernel; 8 / 9 = single-CTA weight-stationary kernel (column-shifted / wide activation units,
- *   R = 3 or 7); 13 = weight-stationary kernel on a CTA pair (cta_group::2, R = 3, one source);
+ *   R = 3 or 7); 13 = weight-stationary kernel on a CTA pair (cta_group::2; R = 3 or 7, up to 3 sources; or a Linear
+ *   (R = 1, H = 1, W = rows % 8 == 0, one source, plain store / residual add) read as an [rows/8, 8] image);
  *   13 + 32*d = the same with bottleneck-probe flags d (tools only, results are NOT valid). */
 int vmgb_conv2d_nhwc_tc(const void* x, const void* x1, const void* x2, int n_src, int x_pitch,
                         const void* w, int Kp, const void* bias,
